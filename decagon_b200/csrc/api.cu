@@ -1,0 +1,1232 @@
+// C ABI of libdecagon_b200.so: graph object, device layout, and the orchestration of one
+// encoder forward / one training step / all-pairs scoring.  See include/decagon_b200.h for the
+// reference interface each entry point replaces.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <memory>
+#include <numeric>
+#include <queue>
+
+#include "dgn_internal.cuh"
+#include "philox.cuh"
+
+using namespace dgn;
+
+namespace {
+
+template <typename T>
+T *dev_alloc(size_t n) {
+    T *p = nullptr;
+    if (n == 0) n = 1;
+    CUDA_CHECK(cudaMalloc(&p, n * sizeof(T)));
+    return p;
+}
+template <typename T>
+T *dev_upload(const std::vector<T> &v) {
+    T *p = dev_alloc<T>(v.size());
+    if (!v.empty()) CUDA_CHECK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return p;
+}
+template <typename T>
+void dev_free(T *&p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+void free_csr(DevCsr &c) {
+    dev_free(c.rowptr);
+    dev_free(c.col);
+    dev_free(c.val);
+}
+void free_seg(SegTable &t) {
+    dev_free(t.seg_row);
+    dev_free(t.seg_begin);
+    dev_free(t.row_seg_ptr);
+    dev_free(t.multi_rows);
+    t = SegTable();
+}
+
+DevCsr upload_csr(const HostCsr &h) {
+    DevCsr d;
+    d.n_rows = h.n_rows;
+    d.nnz = h.nnz();
+    d.rowptr = dev_upload(h.rowptr);
+    d.col = dev_upload(h.col);
+    d.val = dev_upload(h.val);
+    return d;
+}
+
+// every_row: rows without non-zeros still get one (empty) segment so that their result is written
+SegTable build_segments(const HostCsr &h, int seg_len, bool every_row) {
+    SegTable t;
+    t.seg_len = seg_len;
+    int max_row = 0;
+    for (int r = 0; r < h.n_rows; ++r) max_row = std::max(max_row, h.rowptr[r + 1] - h.rowptr[r]);
+    if (every_row && max_row <= seg_len) {
+        t.trivial = true;
+        t.n_seg = h.n_rows;
+        return t;
+    }
+    t.trivial = false;
+    std::vector<int> seg_row, seg_begin, row_seg_ptr((size_t)h.n_rows + 1, 0), multi;
+    for (int r = 0; r < h.n_rows; ++r) {
+        const int b = h.rowptr[r], e = h.rowptr[r + 1];
+        int n = 0;
+        for (int s = b; s < e; s += seg_len) {
+            seg_row.push_back(r);
+            seg_begin.push_back(s);
+            ++n;
+        }
+        if (n == 0 && every_row) {
+            seg_row.push_back(r);
+            seg_begin.push_back(b);
+            n = 1;
+        }
+        if (n > 1) multi.push_back(r);
+        row_seg_ptr[(size_t)r + 1] = row_seg_ptr[r] + n;
+    }
+    t.n_seg = (int)seg_row.size();
+    t.n_multi = (int)multi.size();
+    t.seg_row = dev_upload(seg_row);
+    t.seg_begin = dev_upload(seg_begin);
+    t.row_seg_ptr = dev_upload(row_seg_ptr);
+    t.multi_rows = dev_upload(multi);
+    return t;
+}
+
+struct SlotTable {
+    int n_slots = 0;
+    int *ptr = nullptr, *rel = nullptr;
+};
+
+// longest-processing-time assignment of relations to persistent CTAs, balanced by nnz;
+// inside a slot relations stay in ascending order (fixed summation order)
+SlotTable build_slots(const std::vector<HostCsr> &rels, int n_slots) {
+    const int K = (int)rels.size();
+    n_slots = std::max(1, std::min(n_slots, K));
+    std::vector<int> order(K);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return rels[x].nnz() > rels[y].nnz(); });
+    typedef std::pair<long long, int> Load;
+    std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+    for (int s = 0; s < n_slots; ++s) heap.push(Load(0, s));
+    std::vector<std::vector<int>> lists(n_slots);
+    for (int k : order) {
+        Load l = heap.top();
+        heap.pop();
+        lists[l.second].push_back(k);
+        heap.push(Load(l.first + rels[k].nnz() + rels[k].n_cols, l.second));
+    }
+    std::vector<int> ptr(1, 0), rel;
+    for (auto &l : lists) {
+        std::sort(l.begin(), l.end());
+        rel.insert(rel.end(), l.begin(), l.end());
+        ptr.push_back((int)rel.size());
+    }
+    SlotTable t;
+    t.n_slots = n_slots;
+    t.ptr = dev_upload(ptr);
+    t.rel = dev_upload(rel);
+    return t;
+}
+
+struct NodeType {
+    int n = 0, F = 0;
+    bool feat_set = false, identity = false;
+    std::vector<int> row_groups, col_groups;
+    float *H = nullptr, *Z = nullptr, *dZ = nullptr, *dA = nullptr;
+};
+
+struct Group {
+    int i = 0, j = 0, K = 0, decoder = 0, r0 = 0;
+    int n_i = 0, n_j = 0, F_j = 0;
+    std::vector<HostCsr> rel;
+    std::vector<bool> rel_set;
+    long long nnz = 0;
+    // device sparse structures
+    DevCsr relcsr, fwd, bwd;
+    SegTable fwd_seg, bwd_seg;
+    bool staged = false;
+    SlotTable slots1, slots2;
+    // parameter arena offsets (floats)
+    size_t w1_off = 0, w2_off = 0, glb_off = 0, loc_off = 0, loc_per_rel = 0;
+    // work buffers
+    float *part1 = nullptr, *part2 = nullptr, *Y1 = nullptr, *n1 = nullptr, *Y2 = nullptr, *n2 = nullptr;
+    float *P2 = nullptr, *dS = nullptr, *G2 = nullptr, *bwd_partial = nullptr, *dW2part = nullptr, *dHpart = nullptr;
+    uint32_t *mask1 = nullptr, *mask2 = nullptr;
+    long long mask1_words = 0, mask2_words = 0;
+    int rows_per_chunk = 0, n_row_chunks = 1, rel_per_chunk = 0, n_kchunks = 1;
+    std::vector<uint32_t *> thr;  // per relation
+    std::vector<int> thr_n;
+};
+
+struct Phase {
+    std::string name;
+    cudaEvent_t start, stop;
+};
+
+}  // namespace
+
+struct dgn_graph {
+    int device = 0, n_sm = 148;
+    int n_types = 0, n_groups = 0, R = 0, d1 = 0, d2 = 0, P1 = 0;
+    std::vector<NodeType> types;
+    std::vector<Group> groups;
+    std::vector<std::pair<int, int>> flat;  // r -> (group, k)
+    bool finalized = false;
+    bool allow_staged = true;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // parameters
+    size_t n_params = 0, dec_off = 0;
+    float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
+    float beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f, b1p = 0.9f, b2p = 0.999f;
+    // minibatch staging
+    static const int kRing = 4;
+    int *batch_host[kRing] = {nullptr, nullptr, nullptr, nullptr};
+    long long *neg_host[kRing] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ring_ev[kRing];
+    int ring_cap = 0, ring_pos = 0;
+    int *batch_dev = nullptr;
+    long long *neg_dev = nullptr, *neg_out = nullptr;
+    float *pos_out = nullptr, *negs_out = nullptr, *loss_dev = nullptr, *loss_host = nullptr;
+    int last_B = 0;
+    // measurement
+    bool timing = false;
+    cudaEvent_t timer_start = nullptr, timer_stop = nullptr;
+    std::vector<Phase> phases;
+    long long launches = 0;
+};
+
+namespace {
+
+struct PhaseScope {
+    dgn_graph *g;
+    cudaEvent_t stop = nullptr;
+    PhaseScope(dgn_graph *g_, const char *name, int group = -1) : g(g_) {
+        if (!g->timing) return;
+        Phase p;
+        p.name = name;
+        if (group >= 0) p.name += "/g" + std::to_string(group);
+        CUDA_CHECK(cudaEventCreate(&p.start));
+        CUDA_CHECK(cudaEventCreate(&p.stop));
+        CUDA_CHECK(cudaEventRecord(p.start, g->stream));
+        stop = p.stop;
+        g->phases.push_back(p);
+    }
+    ~PhaseScope() {
+        if (stop) cudaEventRecord(stop, g->stream);
+    }
+};
+
+size_t panel_floats(int P, long long rows) { return (size_t)P * (size_t)rows * 32; }
+
+void check_finalized(dgn_graph *g) { DGN_REQUIRE(g && g->finalized, "graph is not finalized (call dgn_graph_finalize)"); }
+
+void free_group_device(Group &G) {
+    free_csr(G.relcsr);
+    free_csr(G.fwd);
+    free_csr(G.bwd);
+    free_seg(G.fwd_seg);
+    free_seg(G.bwd_seg);
+    dev_free(G.slots1.ptr);
+    dev_free(G.slots1.rel);
+    dev_free(G.slots2.ptr);
+    dev_free(G.slots2.rel);
+    float **bufs[] = {&G.part1, &G.part2, &G.Y1, &G.n1, &G.Y2, &G.n2, &G.P2, &G.dS, &G.G2, &G.bwd_partial, &G.dW2part, &G.dHpart};
+    for (float **b : bufs) dev_free(*b);
+    dev_free(G.mask1);
+    dev_free(G.mask2);
+}
+
+void build_group(dgn_graph *g, Group &G) {
+    free_group_device(G);
+    const int K = G.K, n_i = G.n_i, n_j = G.n_j, P1 = g->P1;
+    G.nnz = 0;
+    for (auto &c : G.rel) G.nnz += c.nnz();
+    DGN_REQUIRE(G.nnz < (long long)INT32_MAX, "group (%d,%d): %lld non-zeros do not fit int32 offsets", G.i, G.j, G.nnz);
+    DGN_REQUIRE((long long)K * std::max(n_j, G.F_j) < (long long)INT32_MAX / 64, "group (%d,%d): K * n_j too large", G.i, G.j);
+
+    // per-relation CSR, concatenated (row pointers hold offsets into the group arrays)
+    HostCsr cat_rel;
+    cat_rel.rowptr.reserve((size_t)K * (n_i + 1));
+    cat_rel.col.reserve((size_t)G.nnz);
+    cat_rel.val.reserve((size_t)G.nnz);
+    for (int k = 0; k < K; ++k) {
+        const int base = (int)cat_rel.col.size();
+        for (int u = 0; u <= n_i; ++u) cat_rel.rowptr.push_back(base + G.rel[k].rowptr[u]);
+        cat_rel.col.insert(cat_rel.col.end(), G.rel[k].col.begin(), G.rel[k].col.end());
+        cat_rel.val.insert(cat_rel.val.end(), G.rel[k].val.begin(), G.rel[k].val.end());
+    }
+    cat_rel.n_rows = K * (n_i + 1) - 1;
+    G.relcsr = upload_csr(cat_rel);
+
+    // forward: [A_0 | A_1 | ...], n_i rows, column = k * n_j + c, entries ordered by (k, c)
+    HostCsr fwd;
+    fwd.n_rows = n_i;
+    fwd.n_cols = K * n_j;
+    fwd.rowptr.assign((size_t)n_i + 1, 0);
+    for (int k = 0; k < K; ++k)
+        for (int u = 0; u < n_i; ++u) fwd.rowptr[(size_t)u + 1] += G.rel[k].rowptr[u + 1] - G.rel[k].rowptr[u];
+    for (int u = 0; u < n_i; ++u) fwd.rowptr[u + 1] += fwd.rowptr[u];
+    fwd.col.resize((size_t)G.nnz);
+    fwd.val.resize((size_t)G.nnz);
+    {
+        std::vector<int> cursor(fwd.rowptr.begin(), fwd.rowptr.end() - 1);
+        for (int k = 0; k < K; ++k)
+            for (int u = 0; u < n_i; ++u)
+                for (int e = G.rel[k].rowptr[u]; e < G.rel[k].rowptr[u + 1]; ++e) {
+                    const int dst = cursor[u]++;
+                    fwd.col[dst] = k * n_j + G.rel[k].col[e];
+                    fwd.val[dst] = G.rel[k].val[e];
+                }
+    }
+    // backward: the transpose, K * n_j rows, column = u
+    HostCsr bwd;
+    csr_transpose(fwd, bwd);
+
+    G.staged = g->allow_staged && staged_supported(n_i, n_j, K) && G.F_j == n_j;
+    const long long target_warps = (long long)g->n_sm * 64 * 2;
+    int seg_len = (int)std::min<long long>(2048, std::max<long long>(64, (G.nnz / target_warps + 31) / 32 * 32));
+    G.fwd = upload_csr(fwd);
+    G.fwd_seg = build_segments(fwd, seg_len, false);
+    G.bwd = upload_csr(bwd);
+    G.bwd_seg = build_segments(bwd, 256, true);
+    if (!G.bwd_seg.trivial) G.bwd_partial = dev_alloc<float>(panel_floats(P1, G.bwd_seg.n_seg));
+
+    if (G.staged) {
+        G.slots1 = build_slots(G.rel, std::max(1, g->n_sm / P1));
+        G.slots2 = build_slots(G.rel, g->n_sm);
+        G.part1 = dev_alloc<float>((size_t)G.slots1.n_slots * panel_floats(P1, n_i));
+        G.part2 = dev_alloc<float>((size_t)G.slots2.n_slots * panel_floats(1, n_i));
+    } else {
+        G.part1 = dev_alloc<float>(panel_floats(P1, G.fwd_seg.n_seg));
+        G.part2 = dev_alloc<float>(panel_floats(1, G.fwd_seg.n_seg));
+    }
+    G.Y1 = dev_alloc<float>(panel_floats(P1, n_i));
+    G.n1 = dev_alloc<float>(n_i);
+    G.Y2 = dev_alloc<float>(panel_floats(1, n_i));
+    G.n2 = dev_alloc<float>(n_i);
+    G.dS = dev_alloc<float>(panel_floats(P1, n_i));
+    G.P2 = dev_alloc<float>(panel_floats(1, (long long)K * n_j));
+    G.G2 = dev_alloc<float>(panel_floats(1, (long long)K * n_j));
+    G.mask1_words = ((long long)K * G.F_j + 31) / 32;
+    G.mask2_words = (long long)K * n_j * P1;
+    G.mask1 = dev_alloc<uint32_t>((size_t)G.mask1_words);
+    G.mask2 = dev_alloc<uint32_t>((size_t)G.mask2_words);
+
+    // dW2: split the n_j rows of one relation into chunks when there are few relations
+    G.n_row_chunks = 1;
+    if ((long long)K < 2LL * g->n_sm) G.n_row_chunks = (int)std::min<long long>((n_j + 511) / 512, (2LL * g->n_sm + K - 1) / K);
+    G.n_row_chunks = std::max(1, G.n_row_chunks);
+    G.rows_per_chunk = ((n_j + G.n_row_chunks - 1) / G.n_row_chunks + 31) / 32 * 32;
+    G.n_row_chunks = (n_j + G.rows_per_chunk - 1) / G.rows_per_chunk;
+    if (G.n_row_chunks > 1) G.dW2part = dev_alloc<float>((size_t)K * G.n_row_chunks * g->d1 * g->d2);
+    // dH: relations are summed inside a chunk, chunks are summed by relu_bwd
+    const int row_tiles = (n_j + 127) / 128;
+    G.n_kchunks = std::max(1, std::min(K, (4 * g->n_sm + row_tiles - 1) / row_tiles));
+    G.rel_per_chunk = (K + G.n_kchunks - 1) / G.n_kchunks;
+    G.n_kchunks = (K + G.rel_per_chunk - 1) / G.rel_per_chunk;
+    G.dHpart = dev_alloc<float>((size_t)G.n_kchunks * panel_floats(P1, n_j));
+}
+
+uint32_t dropout_threshold(float rate) {
+    const double t = ceil((double)rate * 4294967296.0);
+    return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+}
+
+void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step) {
+    const int P1 = g->P1;
+    cudaStream_t s = g->stream;
+    const bool drop = rate > 0.f;
+    const float keep = 1.f - rate;
+    const float scale = drop ? 1.f / keep : 1.f;
+    if (drop) {
+        PhaseScope ph(g, "mask");
+        const uint32_t thr = dropout_threshold(rate);
+        for (auto &G : g->groups) {
+            launch_gen_mask(G.mask1, G.mask1_words, G.F_j, 0, G.r0, kStreamDropout1, step, seed, thr, s);
+            launch_gen_mask(G.mask2, G.mask2_words, (long long)G.n_j * g->d1, G.n_j * P1, G.r0, kStreamDropout2, step, seed, thr, s);
+            g->launches += 2;
+        }
+    }
+    auto spmm_fwd = [&](Group &G, const float *op, int P, long long op_rows, float *part, const SlotTable &slots,
+                        const uint32_t *mask) {
+        if (G.staged) {
+            StagedArgs a = {};
+            a.rowptr = G.relcsr.rowptr, a.col = G.relcsr.col, a.val = G.relcsr.val;
+            a.K = G.K, a.n_i = G.n_i, a.n_j = G.n_j;
+            a.op = op, a.P = P;
+            a.slot_ptr = slots.ptr, a.slot_rel = slots.rel, a.n_slots = slots.n_slots;
+            a.partial = part, a.mask = mask, a.scale = scale;
+            launch_spmm_staged(a, (G.n_i + 31) / 32, s);
+        } else {
+            SpmmArgs a = {};
+            a.rowptr = G.fwd.rowptr, a.col = G.fwd.col, a.val = G.fwd.val;
+            a.seg_row = G.fwd_seg.seg_row, a.seg_begin = G.fwd_seg.seg_begin, a.row_seg_ptr = G.fwd_seg.row_seg_ptr;
+            a.seg_len = G.fwd_seg.seg_len, a.n_seg = G.fwd_seg.n_seg, a.n_rows = G.n_i;
+            a.op = op, a.op_rows = (int)op_rows;
+            a.partial = part, a.force_partial = 1;
+            a.mask = mask, a.col_mask = mask != nullptr, a.scale = scale;
+            launch_spmm(a, P, s);
+        }
+        g->launches++;
+    };
+    auto epilogue = [&](int t, int layer) {
+        NodeType &T = g->types[t];
+        EpiArgs e = {};
+        e.n_rows = T.n;
+        e.relu = layer == 1;
+        e.out = layer == 1 ? T.H : T.Z;
+        DGN_REQUIRE((int)T.row_groups.size() <= kMaxGroupsPerType, "more than %d groups share row type %d", kMaxGroupsPerType, t);
+        for (int gi : T.row_groups) {
+            Group &G = g->groups[gi];
+            EpiGroup &eg = e.g[e.n_groups++];
+            eg.partial = layer == 1 ? G.part1 : G.part2;
+            eg.row_seg_ptr = G.staged ? nullptr : G.fwd_seg.row_seg_ptr;
+            eg.n_slots = layer == 1 ? G.slots1.n_slots : G.slots2.n_slots;
+            eg.Y = layer == 1 ? G.Y1 : G.Y2;
+            eg.nrm = layer == 1 ? G.n1 : G.n2;
+        }
+        launch_node_epilogue(e, layer == 1 ? P1 : 1, s);
+        g->launches++;
+    };
+    for (int gi = 0; gi < g->n_groups; ++gi) {
+        Group &G = g->groups[gi];
+        PhaseScope ph(g, "spmm_fwd1", gi);
+        spmm_fwd(G, g->params + G.w1_off, P1, (long long)G.K * G.F_j, G.part1, G.slots1, drop ? G.mask1 : nullptr);
+    }
+    {
+        PhaseScope ph(g, "epilogue");
+        for (int t = 0; t < g->n_types; ++t) epilogue(t, 1);
+    }
+    for (int gi = 0; gi < g->n_groups; ++gi) {
+        Group &G = g->groups[gi];
+        PhaseScope ph(g, "project", gi);
+        DenseArgs a = {};
+        a.H = g->types[G.j].H, a.W2 = g->params + G.w2_off, a.P2 = G.P2;
+        a.mask = drop ? G.mask2 : nullptr, a.scale = scale, a.K = G.K, a.n_j = G.n_j;
+        launch_project(a, g->d1, g->d2, s);
+        g->launches++;
+    }
+    for (int gi = 0; gi < g->n_groups; ++gi) {
+        Group &G = g->groups[gi];
+        PhaseScope ph(g, "spmm_fwd2", gi);
+        spmm_fwd(G, G.P2, 1, (long long)G.K * G.n_j, G.part2, G.slots2, nullptr);
+    }
+    {
+        PhaseScope ph(g, "epilogue");
+        for (int t = 0; t < g->n_types; ++t) epilogue(t, 2);
+    }
+}
+
+void run_backward(dgn_graph *g, float rate) {
+    const int P1 = g->P1;
+    cudaStream_t s = g->stream;
+    const bool drop = rate > 0.f;
+    const float scale = drop ? 1.f / (1.f - rate) : 1.f;
+    auto spmm_bwd = [&](Group &G, int P, float *out, long long out_rows, const uint32_t *row_mask) {
+        SpmmArgs a = {};
+        a.rowptr = G.bwd.rowptr, a.col = G.bwd.col, a.val = G.bwd.val;
+        a.seg_row = G.bwd_seg.seg_row, a.seg_begin = G.bwd_seg.seg_begin, a.row_seg_ptr = G.bwd_seg.row_seg_ptr;
+        a.seg_len = G.bwd_seg.seg_len, a.n_seg = G.bwd_seg.n_seg, a.n_rows = (int)out_rows;
+        a.op = G.dS, a.op_rows = G.n_i;
+        a.out = out, a.out_rows = (int)out_rows, a.partial = G.bwd_partial;
+        a.mask = row_mask, a.row_mask = row_mask != nullptr, a.scale = scale;
+        launch_spmm(a, P, s);
+        g->launches++;
+        if (G.bwd_seg.n_multi > 0) {
+            launch_seg_reduce(a, G.bwd_seg.multi_rows, G.bwd_seg.n_multi, P, s);
+            g->launches++;
+        }
+    };
+    // ---- layer 2
+    for (int gi = 0; gi < g->n_groups; ++gi) {
+        Group &G = g->groups[gi];
+        {
+            PhaseScope ph(g, "epilogue");
+            L2BwdArgs l = {G.Y2, G.n2, g->types[G.i].dZ, G.dS, G.n_i};
+            launch_l2norm_bwd(l, 1, s);
+            g->launches++;
+        }
+        {
+            PhaseScope ph(g, "spmm_bwd2", gi);
+            spmm_bwd(G, 1, G.G2, (long long)G.K * G.n_j, nullptr);
+        }
+        DenseArgs a = {};
+        a.H = g->types[G.j].H, a.W2 = g->params + G.w2_off, a.G2 = G.G2;
+        a.mask = drop ? G.mask2 : nullptr, a.scale = scale, a.K = G.K, a.n_j = G.n_j;
+        a.rows_per_chunk = G.rows_per_chunk, a.n_row_chunks = G.n_row_chunks;
+        a.rel_per_chunk = G.rel_per_chunk, a.n_kchunks = G.n_kchunks;
+        a.dW2 = G.n_row_chunks > 1 ? G.dW2part : g->grads + G.w2_off;
+        a.dHpart = G.dHpart;
+        {
+            PhaseScope ph(g, "dw2", gi);
+            launch_dw2(a, g->d1, g->d2, s);
+            g->launches++;
+            if (G.n_row_chunks > 1) {
+                launch_dw2_reduce(G.dW2part, g->grads + G.w2_off, G.K, G.n_row_chunks, g->d1 * g->d2, s);
+                g->launches++;
+            }
+        }
+        PhaseScope ph(g, "dh", gi);
+        launch_dh(a, g->d1, g->d2, s);
+        g->launches++;
+    }
+    {
+        PhaseScope ph(g, "epilogue");
+        for (int t = 0; t < g->n_types; ++t) {
+            NodeType &T = g->types[t];
+            ReluBwdArgs r = {};
+            r.n_rows = T.n;
+            r.H = T.H, r.dA = T.dA;
+            for (int gi : T.col_groups) {
+                r.g[r.n_groups].part = g->groups[gi].dHpart;
+                r.g[r.n_groups].n_chunks = g->groups[gi].n_kchunks;
+                r.n_groups++;
+            }
+            launch_relu_bwd(r, P1, s);
+            g->launches++;
+        }
+    }
+    // ---- layer 1
+    for (int gi = 0; gi < g->n_groups; ++gi) {
+        Group &G = g->groups[gi];
+        {
+            PhaseScope ph(g, "epilogue");
+            L2BwdArgs l = {G.Y1, G.n1, g->types[G.i].dA, G.dS, G.n_i};
+            launch_l2norm_bwd(l, P1, s);
+            g->launches++;
+        }
+        PhaseScope ph(g, "spmm_bwd1", gi);
+        spmm_bwd(G, P1, g->grads + G.w1_off, (long long)G.K * G.F_j, drop ? G.mask1 : nullptr);
+    }
+}
+
+// logical [K][rows][32 P] row-major <-> device [P][K * rows][32]
+void pack_panels(const float *src, float *dst, long long stacked_rows, int P) {
+    const int d = 32 * P;
+    for (long long r = 0; r < stacked_rows; ++r)
+        for (int c = 0; c < d; ++c) dst[((size_t)(c >> 5) * stacked_rows + r) * 32 + (c & 31)] = src[(size_t)r * d + c];
+}
+void unpack_panels(const float *src, float *dst, long long stacked_rows, int P) {
+    const int d = 32 * P;
+    for (long long r = 0; r < stacked_rows; ++r)
+        for (int c = 0; c < d; ++c) dst[(size_t)r * d + c] = src[((size_t)(c >> 5) * stacked_rows + r) * 32 + (c & 31)];
+}
+
+struct ParamSpan {
+    size_t off;         // floats into the arena (row-major kinds) or arena offset of the group's W1 block
+    long long count;    // floats covered
+    bool panels;        // W1: panel layout, needs (un)packing
+    long long row0, rows, stacked_rows;
+};
+
+ParamSpan locate_param(dgn_graph *g, int kind, int group, int k) {
+    DGN_REQUIRE(group >= 0 && group < g->n_groups, "group %d out of range", group);
+    Group &G = g->groups[group];
+    DGN_REQUIRE(k >= -1 && k < G.K, "relation index %d out of range for group %d (K = %d)", k, group, G.K);
+    ParamSpan s = {};
+    const long long nk = k < 0 ? G.K : 1, k0 = k < 0 ? 0 : k;
+    switch (kind) {
+        case DGN_PARAM_W1:
+            s.panels = true;
+            s.off = G.w1_off;
+            s.row0 = k0 * G.F_j, s.rows = nk * G.F_j, s.stacked_rows = (long long)G.K * G.F_j;
+            s.count = s.rows * g->d1;
+            break;
+        case DGN_PARAM_W2:
+            s.off = G.w2_off + (size_t)k0 * g->d1 * g->d2;
+            s.count = nk * g->d1 * g->d2;
+            break;
+        case DGN_PARAM_DEC_GLOBAL:
+            DGN_REQUIRE(G.decoder == DGN_DEC_DEDICOM, "group %d has no global_interaction (decoder kind %d)", group, G.decoder);
+            s.off = G.glb_off;
+            s.count = (long long)g->d2 * g->d2;
+            break;
+        case DGN_PARAM_DEC_LOCAL:
+            DGN_REQUIRE(G.loc_per_rel > 0, "group %d (innerproduct) has no per-relation decoder variable", group);
+            s.off = G.loc_off + (size_t)k0 * G.loc_per_rel;
+            s.count = nk * (long long)G.loc_per_rel;
+            break;
+        default: DGN_FAIL(DGN_ERR_INVALID, "unknown parameter kind %d", kind);
+    }
+    return s;
+}
+
+void arena_write(dgn_graph *g, float *arena, const ParamSpan &s, const float *values) {
+    if (!s.panels) {
+        CUDA_CHECK(cudaMemcpy(arena + s.off, values, (size_t)s.count * sizeof(float), cudaMemcpyHostToDevice));
+        return;
+    }
+    // panel p of rows [row0, row0 + rows) is contiguous on the device
+    std::vector<float> tmp((size_t)s.count);
+    pack_panels(values, tmp.data(), s.rows, g->P1);
+    for (int p = 0; p < g->P1; ++p)
+        CUDA_CHECK(cudaMemcpy(arena + s.off + ((size_t)p * s.stacked_rows + s.row0) * 32, tmp.data() + (size_t)p * s.rows * 32,
+                              (size_t)s.rows * 32 * sizeof(float), cudaMemcpyHostToDevice));
+}
+
+void arena_read(dgn_graph *g, const float *arena, const ParamSpan &s, float *values) {
+    CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    if (!s.panels) {
+        CUDA_CHECK(cudaMemcpy(values, arena + s.off, (size_t)s.count * sizeof(float), cudaMemcpyDeviceToHost));
+        return;
+    }
+    std::vector<float> tmp((size_t)s.count);
+    for (int p = 0; p < g->P1; ++p)
+        CUDA_CHECK(cudaMemcpy(tmp.data() + (size_t)p * s.rows * 32, arena + s.off + ((size_t)p * s.stacked_rows + s.row0) * 32,
+                              (size_t)s.rows * 32 * sizeof(float), cudaMemcpyDeviceToHost));
+    unpack_panels(tmp.data(), values, s.rows, g->P1);
+}
+
+void ensure_batch_capacity(dgn_graph *g, int B) {
+    if (B <= g->ring_cap) return;
+    CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    for (int i = 0; i < dgn_graph::kRing; ++i) {
+        if (g->batch_host[i]) cudaFreeHost(g->batch_host[i]);
+        if (g->neg_host[i]) cudaFreeHost(g->neg_host[i]);
+        CUDA_CHECK(cudaMallocHost(&g->batch_host[i], (size_t)B * 2 * sizeof(int)));
+        CUDA_CHECK(cudaMallocHost(&g->neg_host[i], (size_t)B * sizeof(long long)));
+    }
+    dev_free(g->batch_dev);
+    dev_free(g->neg_dev);
+    dev_free(g->neg_out);
+    dev_free(g->pos_out);
+    dev_free(g->negs_out);
+    g->batch_dev = dev_alloc<int>((size_t)B * 2);
+    g->neg_dev = dev_alloc<long long>(B);
+    g->neg_out = dev_alloc<long long>(B);
+    g->pos_out = dev_alloc<float>(B);
+    g->negs_out = dev_alloc<float>(B);
+    g->ring_cap = B;
+}
+
+PredictArgs predict_args(dgn_graph *g, int r, int count) {
+    DGN_REQUIRE(r >= 0 && r + count <= g->R && count >= 1, "relation range [%d, %d) out of range", r, r + count);
+    const int gi = g->flat[r].first, k = g->flat[r].second;
+    DGN_REQUIRE(g->flat[r + count - 1].first == gi, "relations %d..%d span more than one group", r, r + count - 1);
+    Group &G = g->groups[gi];
+    PredictArgs a = {};
+    a.Zi = g->types[G.i].Z, a.Zj = g->types[G.j].Z;
+    a.n_i = G.n_i, a.n_j = G.n_j, a.decoder = G.decoder;
+    a.glb = G.decoder == DGN_DEC_DEDICOM ? g->params + G.glb_off : nullptr;
+    a.loc = G.loc_per_rel ? g->params + G.loc_off + (size_t)k * G.loc_per_rel : nullptr;
+    a.loc_stride = (long long)G.loc_per_rel;
+    a.count = count;
+    return a;
+}
+
+}  // namespace
+
+#define DGN_API_BEGIN try {
+#define DGN_API_END                         \
+    return DGN_OK;                          \
+    }                                       \
+    catch (const Failure &f) { return f.code; } \
+    catch (const std::bad_alloc &) {        \
+        set_error("host allocation failed"); \
+        return DGN_ERR_INVALID;             \
+    }
+
+extern "C" int dgn_device_count(int *count_out) {
+    DGN_API_BEGIN
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    *count_out = n;
+    DGN_API_END
+}
+
+extern "C" int dgn_graph_create(dgn_graph **out, int device, int n_types, const int32_t *n_nodes, const int32_t *feat_dim,
+                                int n_groups, const int32_t *group_ij, const int32_t *group_K,
+                                const int32_t *group_decoder, int hidden1, int hidden2) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(out && n_nodes && feat_dim && group_ij && group_K && group_decoder, "null argument");
+    DGN_REQUIRE(n_types > 0 && n_groups > 0, "need at least one node type and one group");
+    if (hidden2 != 32) DGN_FAIL(DGN_ERR_UNSUPPORTED, "hidden2 = %d is not supported (must be 32)", hidden2);
+    if (hidden1 != 32 && hidden1 != 64 && hidden1 != 128)
+        DGN_FAIL(DGN_ERR_UNSUPPORTED, "hidden1 = %d is not supported (32, 64 or 128)", hidden1);
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        DGN_FAIL(DGN_ERR_NO_DEVICE, "no CUDA device is visible; decagon_b200 has no CPU fallback");
+    }
+    DGN_REQUIRE(device >= 0 && device < n_dev, "device %d out of range (%d visible)", device, n_dev);
+    CUDA_CHECK(cudaSetDevice(device));
+    std::unique_ptr<dgn_graph> g(new dgn_graph());
+    g->device = device;
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    g->n_sm = prop.multiProcessorCount;
+    g->n_types = n_types, g->n_groups = n_groups, g->d1 = hidden1, g->d2 = hidden2, g->P1 = hidden1 / 32;
+    g->types.resize(n_types);
+    for (int t = 0; t < n_types; ++t) {
+        DGN_REQUIRE(n_nodes[t] > 0 && feat_dim[t] > 0, "node type %d: empty", t);
+        g->types[t].n = n_nodes[t];
+        g->types[t].F = feat_dim[t];
+    }
+    g->groups.resize(n_groups);
+    size_t off = 0;
+    int r = 0;
+    for (int gi = 0; gi < n_groups; ++gi) {
+        Group &G = g->groups[gi];
+        G.i = group_ij[2 * gi], G.j = group_ij[2 * gi + 1], G.K = group_K[gi], G.decoder = group_decoder[gi];
+        DGN_REQUIRE(G.i >= 0 && G.i < n_types && G.j >= 0 && G.j < n_types, "group %d: node types (%d, %d) out of range", gi, G.i, G.j);
+        DGN_REQUIRE(G.K > 0, "group %d: no relations", gi);
+        DGN_REQUIRE(G.decoder >= DGN_DEC_INNERPRODUCT && G.decoder <= DGN_DEC_DEDICOM, "Unknown decoder type %d", G.decoder);
+        G.n_i = n_nodes[G.i], G.n_j = n_nodes[G.j], G.F_j = feat_dim[G.j];
+        G.r0 = r;
+        G.rel.resize(G.K);
+        G.rel_set.assign(G.K, false);
+        G.thr.assign(G.K, nullptr);
+        G.thr_n.assign(G.K, 0);
+        for (int k = 0; k < G.K; ++k) g->flat.push_back(std::make_pair(gi, k));
+        r += G.K;
+        g->types[G.i].row_groups.push_back(gi);
+        g->types[G.j].col_groups.push_back(gi);
+        G.w1_off = off;
+        off += (size_t)G.K * G.F_j * hidden1;
+    }
+    g->R = r;
+    for (auto &G : g->groups) {
+        G.w2_off = off;
+        off += (size_t)G.K * hidden1 * hidden2;
+    }
+    g->dec_off = off;
+    for (auto &G : g->groups) {
+        if (G.decoder == DGN_DEC_DEDICOM) {
+            G.glb_off = off;
+            off += (size_t)hidden2 * hidden2;
+        }
+        G.loc_per_rel = G.decoder == DGN_DEC_BILINEAR ? (size_t)hidden2 * hidden2 : G.decoder == DGN_DEC_INNERPRODUCT ? 0 : (size_t)hidden2;
+        G.loc_off = off;
+        off += (size_t)G.K * G.loc_per_rel;
+    }
+    g->n_params = off;
+    g->params = dev_alloc<float>(off);
+    g->grads = dev_alloc<float>(off);
+    g->adam_m = dev_alloc<float>(off);
+    g->adam_v = dev_alloc<float>(off);
+    CUDA_CHECK(cudaMemset(g->params, 0, off * sizeof(float)));
+    CUDA_CHECK(cudaMemset(g->grads, 0, off * sizeof(float)));
+    CUDA_CHECK(cudaMemset(g->adam_m, 0, off * sizeof(float)));
+    CUDA_CHECK(cudaMemset(g->adam_v, 0, off * sizeof(float)));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+    g->own_stream = true;
+    for (int i = 0; i < dgn_graph::kRing; ++i) CUDA_CHECK(cudaEventCreateWithFlags(&g->ring_ev[i], cudaEventDisableTiming));
+    g->loss_dev = dev_alloc<float>(1);
+    CUDA_CHECK(cudaMallocHost(&g->loss_host, sizeof(float)));
+    for (int t = 0; t < n_types; ++t) {
+        NodeType &T = g->types[t];
+        T.H = dev_alloc<float>(panel_floats(g->P1, T.n));
+        T.dA = dev_alloc<float>(panel_floats(g->P1, T.n));
+        T.Z = dev_alloc<float>(panel_floats(1, T.n));
+        T.dZ = dev_alloc<float>(panel_floats(1, T.n));
+        CUDA_CHECK(cudaMemset(T.dZ, 0, panel_floats(1, T.n) * sizeof(float)));
+    }
+    const char *env = getenv("DGN_DISABLE_STAGED");
+    g->allow_staged = !(env && env[0] == '1');
+    *out = g.release();
+    DGN_API_END
+}
+
+extern "C" int dgn_graph_destroy(dgn_graph *g) {
+    DGN_API_BEGIN
+    if (!g) return DGN_OK;
+    cudaSetDevice(g->device);
+    cudaDeviceSynchronize();
+    for (auto &G : g->groups) {
+        free_group_device(G);
+        for (auto &t : G.thr) dev_free(t);
+    }
+    for (auto &T : g->types) {
+        dev_free(T.H);
+        dev_free(T.Z);
+        dev_free(T.dZ);
+        dev_free(T.dA);
+    }
+    dev_free(g->params);
+    dev_free(g->grads);
+    dev_free(g->adam_m);
+    dev_free(g->adam_v);
+    dev_free(g->batch_dev);
+    dev_free(g->neg_dev);
+    dev_free(g->neg_out);
+    dev_free(g->pos_out);
+    dev_free(g->negs_out);
+    dev_free(g->loss_dev);
+    if (g->loss_host) cudaFreeHost(g->loss_host);
+    for (int i = 0; i < dgn_graph::kRing; ++i) {
+        if (g->batch_host[i]) cudaFreeHost(g->batch_host[i]);
+        if (g->neg_host[i]) cudaFreeHost(g->neg_host[i]);
+        cudaEventDestroy(g->ring_ev[i]);
+    }
+    for (auto &p : g->phases) {
+        cudaEventDestroy(p.start);
+        cudaEventDestroy(p.stop);
+    }
+    if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
+    delete g;
+    DGN_API_END
+}
+
+extern "C" int dgn_graph_set_relation(dgn_graph *g, int r, int32_t n_rows, int32_t n_cols, int64_t nnz,
+                                      const int32_t *coo_rows, const int32_t *coo_cols, const float *vals) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(g, "null graph");
+    DGN_REQUIRE(r >= 0 && r < g->R, "relation %d out of range (R = %d)", r, g->R);
+    Group &G = g->groups[g->flat[r].first];
+    DGN_REQUIRE(n_rows == G.n_i && n_cols == G.n_j, "relation %d: shape %d x %d does not match group (%d,%d): %d x %d", r, n_rows,
+                n_cols, G.i, G.j, G.n_i, G.n_j);
+    csr_from_coo(n_rows, n_cols, nnz, coo_rows, coo_cols, vals, G.rel[g->flat[r].second]);
+    G.rel_set[g->flat[r].second] = true;
+    g->finalized = false;
+    DGN_API_END
+}
+
+extern "C" int dgn_graph_set_features(dgn_graph *g, int type, int32_t n_rows, int32_t n_cols, int64_t nnz,
+                                      const int32_t *coo_rows, const int32_t *coo_cols, const float *vals) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(g, "null graph");
+    DGN_REQUIRE(type >= 0 && type < g->n_types, "node type %d out of range", type);
+    NodeType &T = g->types[type];
+    DGN_REQUIRE(n_rows == T.n && n_cols == T.F, "features of type %d: shape %d x %d, expected %d x %d", type, n_rows, n_cols, T.n, T.F);
+    bool identity = n_rows == n_cols && nnz == n_rows;
+    std::vector<char> seen((size_t)n_rows, 0);
+    for (int64_t e = 0; identity && e < nnz; ++e) {
+        identity = coo_rows[e] == coo_cols[e] && coo_rows[e] >= 0 && coo_rows[e] < n_rows && vals[e] == 1.f && !seen[coo_rows[e]];
+        if (identity) seen[coo_rows[e]] = 1;
+    }
+    if (!identity)
+        DGN_FAIL(DGN_ERR_UNSUPPORTED,
+                 "features of type %d are not the identity: general sparse features are not implemented yet "
+                 "(SURVEY.md 8f rank 2); every BASELINE config uses identity features", type);
+    T.identity = true;
+    T.feat_set = true;
+    g->finalized = false;
+    DGN_API_END
+}
+
+extern "C" int dgn_sampler_set_degrees(dgn_graph *g, int r, const double *degrees, int32_t n) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(g, "null graph");
+    DGN_REQUIRE(r >= 0 && r < g->R, "relation %d out of range", r);
+    Group &G = g->groups[g->flat[r].first];
+    const int k = g->flat[r].second;
+    DGN_REQUIRE(n == G.n_i, "relation %d: %d degrees, row type has %d nodes (range_max = len(degrees[i][k]), optimizer.py:45)", r, n, G.n_i);
+    std::vector<uint32_t> thr((size_t)n);
+    int rc = dgn_sampler_thresholds(degrees, n, thr.data());
+    if (rc != DGN_OK) return rc;
+    CUDA_CHECK(cudaSetDevice(g->device));
+    dev_free(G.thr[k]);
+    G.thr[k] = dev_upload(thr);
+    G.thr_n[k] = n;
+    DGN_API_END
+}
+
+extern "C" int dgn_graph_finalize(dgn_graph *g) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(g, "null graph");
+    CUDA_CHECK(cudaSetDevice(g->device));
+    for (auto &G : g->groups) {
+        for (int k = 0; k < G.K; ++k) DGN_REQUIRE(G.rel_set[k], "relation (%d,%d,%d) was never set", G.i, G.j, k);
+        DGN_REQUIRE(g->types[G.j].feat_set, "features of node type %d were never set", G.j);
+        DGN_REQUIRE(G.F_j == G.n_j, "identity features need feat_dim == n_nodes for type %d", G.j);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    for (auto &G : g->groups) build_group(g, G);
+    g->finalized = true;
+    DGN_API_END
+}
+
+extern "C" int dgn_graph_relation_nnz(dgn_graph *g, int r, int64_t *nnz_out) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(g && r >= 0 && r < g->R, "relation %d out of range", r);
+    *nnz_out = g->groups[g->flat[r].first].rel[g->flat[r].second].nnz();
+    DGN_API_END
+}
+
+extern "C" int dgn_graph_get_csr(dgn_graph *g, int r, int32_t *rowptr_out, int32_t *col_out, float *val_out) {
+    DGN_API_BEGIN
+    check_finalized(g);
+    DGN_REQUIRE(r >= 0 && r < g->R, "relation %d out of range", r);
+    CUDA_CHECK(cudaSetDevice(g->device));
+    Group &G = g->groups[g->flat[r].first];
+    const int k = g->flat[r].second;
+    std::vector<int> rp((size_t)G.n_i + 1);
+    CUDA_CHECK(cudaMemcpy(rp.data(), G.relcsr.rowptr + (size_t)k * (G.n_i + 1), rp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    const int base = rp[0], nnz = rp[G.n_i] - base;
+    for (int u = 0; u <= G.n_i; ++u) rowptr_out[u] = rp[u] - base;
+    CUDA_CHECK(cudaMemcpy(col_out, G.relcsr.col + base, (size_t)nnz * sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(val_out, G.relcsr.val + base, (size_t)nnz * sizeof(float), cudaMemcpyDeviceToHost));
+    DGN_API_END
+}
+
+extern "C" int dgn_params_set(dgn_graph *g, int kind, int group, int k, const float *values, int64_t n) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(g && values, "null argument");
+    CUDA_CHECK(cudaSetDevice(g->device));
+    ParamSpan s = locate_param(g, kind, group, k);
+    DGN_REQUIRE(n == s.count, "parameter kind %d group %d k %d: got %lld floats, expected %lld", kind, group, k, (long long)n, s.count);
+    CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    arena_write(g, g->params, s, values);
+    DGN_API_END
+}
+
+extern "C" int dgn_params_get(dgn_graph *g, int kind, int group, int k, float *values_out, int64_t n) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(g && values_out, "null argument");
+    CUDA_CHECK(cudaSetDevice(g->device));
+    ParamSpan s = locate_param(g, kind, group, k);
+    DGN_REQUIRE(n == s.count, "parameter kind %d group %d k %d: got %lld floats, expected %lld", kind, group, k, (long long)n, s.count);
+    arena_read(g, g->params, s, values_out);
+    DGN_API_END
+}
+
+extern "C" int dgn_grads_get(dgn_graph *g, int kind, int group, int k, float *values_out, int64_t n) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(g && values_out, "null argument");
+    CUDA_CHECK(cudaSetDevice(g->device));
+    ParamSpan s = locate_param(g, kind, group, k);
+    DGN_REQUIRE(n == s.count, "gradient kind %d group %d k %d: got %lld floats, expected %lld", kind, group, k, (long long)n, s.count);
+    arena_read(g, g->grads, s, values_out);
+    DGN_API_END
+}
+
+extern "C" int dgn_params_count(dgn_graph *g, int64_t *n_out) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(g && n_out, "null argument");
+    *n_out = (int64_t)g->n_params;
+    DGN_API_END
+}
+
+extern "C" int dgn_optimizer_reset(dgn_graph *g, float beta1, float beta2, float epsilon) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(g, "null graph");
+    CUDA_CHECK(cudaSetDevice(g->device));
+    CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    CUDA_CHECK(cudaMemset(g->adam_m, 0, g->n_params * sizeof(float)));
+    CUDA_CHECK(cudaMemset(g->adam_v, 0, g->n_params * sizeof(float)));
+    g->beta1 = beta1, g->beta2 = beta2, g->eps = epsilon;
+    g->b1p = beta1, g->b2p = beta2;
+    DGN_API_END
+}
+
+extern "C" int dgn_encoder_forward(dgn_graph *g, float dropout, uint64_t seed, uint32_t step) {
+    DGN_API_BEGIN
+    check_finalized(g);
+    DGN_REQUIRE(dropout >= 0.f && dropout < 1.f, "dropout rate %g outside [0, 1)", dropout);
+    CUDA_CHECK(cudaSetDevice(g->device));
+    run_forward(g, dropout, seed, step);
+    DGN_API_END
+}
+
+extern "C" int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t batch_size, const int64_t *negatives,
+                              int loss_kind, float margin, float neg_weight, float learning_rate, float dropout,
+                              uint64_t seed, uint32_t step, int apply_update, float *loss_out) {
+    DGN_API_BEGIN
+    check_finalized(g);
+    DGN_REQUIRE(batch && batch_size > 0, "empty batch");
+    DGN_REQUIRE(r >= 0 && r < g->R, "batch_edge_type_idx %d out of range (R = %d)", r, g->R);
+    DGN_REQUIRE(loss_kind == DGN_LOSS_HINGE || loss_kind == DGN_LOSS_XENT, "unknown loss kind %d", loss_kind);
+    DGN_REQUIRE(dropout >= 0.f && dropout < 1.f, "dropout rate %g outside [0, 1)", dropout);
+    CUDA_CHECK(cudaSetDevice(g->device));
+    Group &G = g->groups[g->flat[r].first];
+    const int k = g->flat[r].second;
+    DGN_REQUIRE(negatives != nullptr || G.thr[k] != nullptr,
+                "relation %d: no negatives given and no degree table set (dgn_sampler_set_degrees)", r);
+    for (int b = 0; b < batch_size; ++b) {
+        DGN_REQUIRE(batch[2 * b] >= 0 && batch[2 * b] < G.n_i && batch[2 * b + 1] >= 0 && batch[2 * b + 1] < G.n_j,
+                    "batch edge %d = (%d, %d) outside %d x %d", b, batch[2 * b], batch[2 * b + 1], G.n_i, G.n_j);
+        if (negatives) DGN_REQUIRE(negatives[b] >= 0 && negatives[b] < G.n_i, "negative sample %d = %lld outside [0, %d)", b, (long long)negatives[b], G.n_i);
+    }
+    cudaStream_t s = g->stream;
+    ensure_batch_capacity(g, batch_size);
+    const int slot = g->ring_pos;
+    g->ring_pos = (g->ring_pos + 1) % dgn_graph::kRing;
+    CUDA_CHECK(cudaEventSynchronize(g->ring_ev[slot]));
+    memcpy(g->batch_host[slot], batch, (size_t)batch_size * 2 * sizeof(int));
+    CUDA_CHECK(cudaMemcpyAsync(g->batch_dev, g->batch_host[slot], (size_t)batch_size * 2 * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (negatives) {
+        memcpy(g->neg_host[slot], negatives, (size_t)batch_size * sizeof(long long));
+        CUDA_CHECK(cudaMemcpyAsync(g->neg_dev, g->neg_host[slot], (size_t)batch_size * sizeof(long long), cudaMemcpyHostToDevice, s));
+    }
+    CUDA_CHECK(cudaEventRecord(g->ring_ev[slot], s));
+
+    run_forward(g, dropout, seed, step);
+
+    {
+        PhaseScope ph(g, "decode");
+        for (auto &T : g->types) CUDA_CHECK(cudaMemsetAsync(T.dZ, 0, panel_floats(1, T.n) * sizeof(float), s));
+        if (g->n_params > g->dec_off)
+            CUDA_CHECK(cudaMemsetAsync(g->grads + g->dec_off, 0, (g->n_params - g->dec_off) * sizeof(float), s));
+        DecodeArgs a = {};
+        a.Zi = g->types[G.i].Z, a.Zj = g->types[G.j].Z, a.dZi = g->types[G.i].dZ, a.dZj = g->types[G.j].dZ;
+        a.n_i = G.n_i, a.n_j = G.n_j;
+        a.batch = g->batch_dev, a.neg_in = negatives ? g->neg_dev : nullptr, a.neg_out = g->neg_out;
+        a.thr = G.thr[k], a.n_thr = G.thr_n[k];
+        a.B = batch_size, a.decoder = G.decoder, a.loss_kind = loss_kind, a.margin = margin, a.neg_weight = neg_weight;
+        a.glb = G.decoder == DGN_DEC_DEDICOM ? g->params + G.glb_off : nullptr;
+        a.loc = G.loc_per_rel ? g->params + G.loc_off + (size_t)k * G.loc_per_rel : nullptr;
+        a.g_glb = G.decoder == DGN_DEC_DEDICOM ? g->grads + G.glb_off : nullptr;
+        a.g_loc = G.loc_per_rel ? g->grads + G.loc_off + (size_t)k * G.loc_per_rel : nullptr;
+        a.pos_out = g->pos_out, a.neg_score_out = g->negs_out, a.loss_out = g->loss_dev;
+        a.seed_lo = (uint32_t)(seed & 0xffffffffu), a.seed_hi = (uint32_t)(seed >> 32), a.step = step, a.relation = (uint32_t)r;
+        launch_decode(a, s);
+        g->launches++;
+        g->last_B = batch_size;
+    }
+
+    run_backward(g, dropout);
+
+    if (apply_update) {
+        PhaseScope ph(g, "adam");
+        // TF 1.8 ApplyAdam: alpha = lr * sqrt(1 - beta2^t) / (1 - beta1^t), float32
+        const float alpha = learning_rate * sqrtf(1.f - g->b2p) / (1.f - g->b1p);
+        launch_adam(g->params, g->grads, g->adam_m, g->adam_v, (long long)g->n_params, alpha, 1.f - g->beta1, 1.f - g->beta2, g->eps, s);
+        g->launches++;
+        g->b1p *= g->beta1;
+        g->b2p *= g->beta2;
+    }
+    if (loss_out) {
+        CUDA_CHECK(cudaMemcpyAsync(g->loss_host, g->loss_dev, sizeof(float), cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        *loss_out = *g->loss_host;
+    }
+    DGN_API_END
+}
+
+extern "C" int dgn_last_batch_outputs(dgn_graph *g, float *pos_out, float *neg_out, int64_t *neg_samples_out,
+                                      int32_t batch_size) {
+    DGN_API_BEGIN
+    check_finalized(g);
+    DGN_REQUIRE(batch_size == g->last_B && batch_size > 0, "batch size %d does not match the last step (%d)", batch_size, g->last_B);
+    CUDA_CHECK(cudaSetDevice(g->device));
+    CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    if (pos_out) CUDA_CHECK(cudaMemcpy(pos_out, g->pos_out, (size_t)batch_size * sizeof(float), cudaMemcpyDeviceToHost));
+    if (neg_out) CUDA_CHECK(cudaMemcpy(neg_out, g->negs_out, (size_t)batch_size * sizeof(float), cudaMemcpyDeviceToHost));
+    if (neg_samples_out)
+        CUDA_CHECK(cudaMemcpy(neg_samples_out, g->neg_out, (size_t)batch_size * sizeof(long long), cudaMemcpyDeviceToHost));
+    DGN_API_END
+}
+
+extern "C" int dgn_predict_all_pairs(dgn_graph *g, int r, float *out) {
+    DGN_API_BEGIN
+    check_finalized(g);
+    DGN_REQUIRE(out, "null output");
+    CUDA_CHECK(cudaSetDevice(g->device));
+    PredictArgs a = predict_args(g, r, 1);
+    const size_t n = (size_t)a.n_i * a.n_j;
+    float *tmp = dev_alloc<float>(n);
+    a.out = tmp;
+    try {
+        launch_predict(a, g->stream);
+        g->launches++;
+        CUDA_CHECK(cudaStreamSynchronize(g->stream));
+        CUDA_CHECK(cudaMemcpy(out, tmp, n * sizeof(float), cudaMemcpyDeviceToHost));
+    } catch (...) {
+        cudaFree(tmp);
+        throw;
+    }
+    cudaFree(tmp);
+    DGN_API_END
+}
+
+extern "C" int dgn_predict_relations_dev(dgn_graph *g, int r0, int count, float *out_dev) {
+    DGN_API_BEGIN
+    check_finalized(g);
+    DGN_REQUIRE(out_dev, "null output");
+    CUDA_CHECK(cudaSetDevice(g->device));
+    PredictArgs a = predict_args(g, r0, count);
+    a.out = out_dev;
+    PhaseScope ph(g, "predict");
+    launch_predict(a, g->stream);
+    g->launches++;
+    DGN_API_END
+}
+
+extern "C" int dgn_predict_edges(dgn_graph *g, int r, const int32_t *edges, int32_t n_edges, int apply_sigmoid, float *out) {
+    DGN_API_BEGIN
+    check_finalized(g);
+    DGN_REQUIRE(n_edges >= 0 && (n_edges == 0 || (edges && out)), "null argument");
+    if (n_edges == 0) return DGN_OK;
+    CUDA_CHECK(cudaSetDevice(g->device));
+    PredictArgs a = predict_args(g, r, 1);
+    for (int e = 0; e < n_edges; ++e)
+        DGN_REQUIRE(edges[2 * e] >= 0 && edges[2 * e] < a.n_i && edges[2 * e + 1] >= 0 && edges[2 * e + 1] < a.n_j,
+                    "edge %d = (%d, %d) outside %d x %d", e, edges[2 * e], edges[2 * e + 1], a.n_i, a.n_j);
+    int *e_dev = dev_alloc<int>((size_t)n_edges * 2);
+    float *o_dev = dev_alloc<float>(n_edges);
+    try {
+        CUDA_CHECK(cudaMemcpyAsync(e_dev, edges, (size_t)n_edges * 2 * sizeof(int), cudaMemcpyHostToDevice, g->stream));
+        launch_predict_edges(a, e_dev, n_edges, apply_sigmoid, o_dev, g->stream);
+        g->launches++;
+        CUDA_CHECK(cudaMemcpyAsync(out, o_dev, (size_t)n_edges * sizeof(float), cudaMemcpyDeviceToHost, g->stream));
+        CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    } catch (...) {
+        cudaFree(e_dev);
+        cudaFree(o_dev);
+        throw;
+    }
+    cudaFree(e_dev);
+    cudaFree(o_dev);
+    DGN_API_END
+}
+
+extern "C" int dgn_tensor_get(dgn_graph *g, int which, int index, float *out, int64_t n) {
+    DGN_API_BEGIN
+    check_finalized(g);
+    DGN_REQUIRE(out, "null output");
+    CUDA_CHECK(cudaSetDevice(g->device));
+    const float *src = nullptr;
+    long long rows = 0;
+    int P = 1;
+    switch (which) {
+        case DGN_TENSOR_HIDDEN1:
+        case DGN_TENSOR_EMBEDDINGS:
+        case DGN_TENSOR_GRAD_EMBEDDINGS: {
+            DGN_REQUIRE(index >= 0 && index < g->n_types, "node type %d out of range", index);
+            NodeType &T = g->types[index];
+            rows = T.n;
+            if (which == DGN_TENSOR_HIDDEN1) src = T.H, P = g->P1;
+            else src = which == DGN_TENSOR_EMBEDDINGS ? T.Z : T.dZ;
+        } break;
+        case DGN_TENSOR_LAYER1_GROUP:
+        case DGN_TENSOR_LAYER2_GROUP: {
+            DGN_REQUIRE(index >= 0 && index < g->n_groups, "group %d out of range", index);
+            Group &G = g->groups[index];
+            rows = G.n_i;
+            if (which == DGN_TENSOR_LAYER1_GROUP) src = G.Y1, P = g->P1;
+            else src = G.Y2;
+        } break;
+        default: DGN_FAIL(DGN_ERR_INVALID, "unknown tensor id %d", which);
+    }
+    DGN_REQUIRE(n == rows * 32 * P, "tensor %d[%d]: got room for %lld floats, need %lld", which, index, (long long)n, rows * 32 * P);
+    CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    std::vector<float> tmp((size_t)n);
+    CUDA_CHECK(cudaMemcpy(tmp.data(), src, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    unpack_panels(tmp.data(), out, rows, P);
+    DGN_API_END
+}
+
+extern "C" int dgn_relation_matrices(dgn_graph *g, int r, float *glb_out, float *loc_out) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(g && glb_out && loc_out, "null argument");
+    DGN_REQUIRE(r >= 0 && r < g->R, "relation %d out of range", r);
+    CUDA_CHECK(cudaSetDevice(g->device));
+    Group &G = g->groups[g->flat[r].first];
+    const int k = g->flat[r].second;
+    const size_t n = (size_t)g->d2 * g->d2;
+    float *tmp = dev_alloc<float>(2 * n);
+    try {
+        launch_relation_matrices(G.decoder, G.decoder == DGN_DEC_DEDICOM ? g->params + G.glb_off : nullptr,
+                                 G.loc_per_rel ? g->params + G.loc_off + (size_t)k * G.loc_per_rel : nullptr, tmp, tmp + n, g->stream);
+        g->launches++;
+        CUDA_CHECK(cudaStreamSynchronize(g->stream));
+        CUDA_CHECK(cudaMemcpy(glb_out, tmp, n * sizeof(float), cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(loc_out, tmp + n, n * sizeof(float), cudaMemcpyDeviceToHost));
+    } catch (...) {
+        cudaFree(tmp);
+        throw;
+    }
+    cudaFree(tmp);
+    DGN_API_END
+}
+
+extern "C" int dgn_sync(dgn_graph *g) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(g, "null graph");
+    CUDA_CHECK(cudaSetDevice(g->device));
+    CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    DGN_API_END
+}
+
+extern "C" int dgn_timing_enable(dgn_graph *g, int enable) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(g, "null graph");
+    g->timing = enable != 0;
+    DGN_API_END
+}
+
+extern "C" int dgn_timing_reset(dgn_graph *g) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(g, "null graph");
+    CUDA_CHECK(cudaSetDevice(g->device));
+    CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    for (auto &p : g->phases) {
+        cudaEventDestroy(p.start);
+        cudaEventDestroy(p.stop);
+    }
+    g->phases.clear();
+    g->launches = 0;
+    DGN_API_END
+}
+
+extern "C" int dgn_timing_get(dgn_graph *g, const char *name, double *ms_out, int64_t *count_out) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(g && name && ms_out, "null argument");
+    CUDA_CHECK(cudaSetDevice(g->device));
+    CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    double total = 0.0;
+    int64_t count = 0;
+    const size_t len = strlen(name);
+    for (auto &p : g->phases)
+        if (p.name.compare(0, len, name) == 0) {
+            float ms = 0.f;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, p.start, p.stop));
+            total += ms;
+            ++count;
+        }
+    *ms_out = total;
+    if (count_out) *count_out = count;
+    DGN_API_END
+}
+
+extern "C" int dgn_launch_count(dgn_graph *g, int64_t *launches_out) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(g && launches_out, "null argument");
+    *launches_out = g->launches;
+    DGN_API_END
+}
+
+// whole-region timer on the library's own stream (bench.py: CUDA events around K steps)
+extern "C" int dgn_timer_start(dgn_graph *g) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(g, "null graph");
+    CUDA_CHECK(cudaSetDevice(g->device));
+    if (!g->timer_start) {
+        CUDA_CHECK(cudaEventCreate(&g->timer_start));
+        CUDA_CHECK(cudaEventCreate(&g->timer_stop));
+    }
+    CUDA_CHECK(cudaEventRecord(g->timer_start, g->stream));
+    DGN_API_END
+}
+
+extern "C" int dgn_timer_stop(dgn_graph *g, double *ms_out) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(g && ms_out && g->timer_start, "timer was not started");
+    CUDA_CHECK(cudaSetDevice(g->device));
+    CUDA_CHECK(cudaEventRecord(g->timer_stop, g->stream));
+    CUDA_CHECK(cudaEventSynchronize(g->timer_stop));
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, g->timer_start, g->timer_stop));
+    *ms_out = ms;
+    DGN_API_END
+}
+
+extern "C" int dgn_memory_bytes(dgn_graph *g, int64_t *free_out, int64_t *total_out) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(g && free_out && total_out, "null argument");
+    CUDA_CHECK(cudaSetDevice(g->device));
+    size_t f = 0, t = 0;
+    CUDA_CHECK(cudaMemGetInfo(&f, &t));
+    *free_out = (int64_t)f, *total_out = (int64_t)t;
+    DGN_API_END
+}

@@ -1,0 +1,206 @@
+// Internal declarations shared by the translation units of libdecagon_b200.so.
+// Everything device-side is written for sm_100a (B200); there is no CPU fallback.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/decagon_b200.h"
+
+namespace dgn {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char *fmt, ...);
+struct Failure {
+    int code;
+};
+#define DGN_FAIL(code_, ...)          \
+    do {                              \
+        ::dgn::set_error(__VA_ARGS__); \
+        throw ::dgn::Failure{code_};  \
+    } while (0)
+#define DGN_REQUIRE(cond, ...) \
+    do {                       \
+        if (!(cond)) DGN_FAIL(DGN_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+#define CUDA_CHECK(expr)                                                                            \
+    do {                                                                                            \
+        cudaError_t err__ = (expr);                                                                 \
+        if (err__ != cudaSuccess)                                                                   \
+            DGN_FAIL(DGN_ERR_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,             \
+                     cudaGetErrorString(err__));                                                    \
+    } while (0)
+
+// ---------------------------------------------------------------- host-side sparse structures
+struct HostCsr {
+    int n_rows = 0, n_cols = 0;
+    std::vector<int> rowptr, col;
+    std::vector<float> val;
+    int64_t nnz() const { return (int64_t)col.size(); }
+};
+void csr_from_coo(int n_rows, int n_cols, int64_t nnz, const int32_t *rows, const int32_t *cols, const float *vals,
+                  HostCsr &out);
+void csr_transpose(const HostCsr &a, HostCsr &out);
+
+struct DevCsr {
+    int n_rows = 0;
+    int64_t nnz = 0;
+    int *rowptr = nullptr, *col = nullptr;
+    float *val = nullptr;
+};
+
+// Rows cut into segments of at most seg_len non-zeros; one warp per segment.
+// trivial: every row fits one segment and no table is stored (segment id == row id).
+struct SegTable {
+    bool trivial = true;
+    int seg_len = 0;
+    int n_seg = 0;
+    int n_multi = 0;              // rows that span more than one segment
+    int *seg_row = nullptr;       // [n_seg]
+    int *seg_begin = nullptr;     // [n_seg]
+    int *row_seg_ptr = nullptr;   // [n_rows + 1]
+    int *multi_rows = nullptr;    // [n_multi]
+};
+
+// ---------------------------------------------------------------- device-side argument blocks
+constexpr int kMaxGroupsPerType = 8;
+constexpr float kL2Eps = 1e-12f;  // tf.nn.l2_normalize epsilon (layers.py:93,117)
+
+struct SpmmArgs {
+    // sparse operand
+    const int *rowptr, *col;
+    const float *val;
+    const int *seg_row, *seg_begin, *row_seg_ptr;  // null when the table is trivial
+    int seg_len, n_seg, n_rows;
+    // dense operand, panel layout [P][op_rows][32]
+    const float *op;
+    int op_rows;
+    // result: direct rows go to out[P][out_rows][32]; rows split over segments go to
+    // partial[n_seg][P][32] (force_partial: every segment goes to partial)
+    float *out;
+    int out_rows;
+    float *partial;
+    int force_partial;
+    // dropout of the layer-1 feature rows (identity features): bit index = column (col_mask)
+    // or = output row (row_mask); kept entries are scaled by `scale`
+    const uint32_t *mask;
+    int col_mask, row_mask;
+    float scale;
+};
+
+struct StagedArgs {
+    // per-relation CSR of the group, concatenated: rowptr[K][n_i + 1] holds offsets into col/val
+    const int *rowptr, *col;
+    const float *val;
+    int K, n_i, n_j;
+    // operand tiles: tile (p, k) = op[((p * K + k) * n_j) * 32 ...], n_j * 32 floats
+    const float *op;
+    int P;
+    // work lists: slot s handles relations slot_rel[slot_ptr[s] .. slot_ptr[s+1])
+    const int *slot_ptr, *slot_rel;
+    int n_slots;
+    float *partial;  // [n_slots][P][n_i][32]
+    const uint32_t *mask;  // layer-1 dropout bits, bit index k * n_j + c (null: none)
+    float scale;
+};
+
+struct EpiGroup {
+    const float *partial;
+    const int *row_seg_ptr;  // segment mode; null => slot mode
+    int n_slots;             // slot mode: partial[n_slots][P][n_rows][32]
+    float *Y;                // [P][n_rows][32] normalised rows
+    float *nrm;              // [n_rows]  sqrt(max(|S|^2, eps))
+};
+struct EpiArgs {
+    int n_rows, n_groups, relu;
+    EpiGroup g[kMaxGroupsPerType];
+    float *out;  // [P][n_rows][32]
+};
+
+struct L2BwdArgs {  // dS = l2norm backward of one group
+    const float *Y, *nrm, *dY;
+    float *dS;
+    int n_rows;
+};
+
+struct ReluBwdGroup {
+    const float *part;  // [n_chunks][P][n_rows][32]
+    int n_chunks;
+};
+struct ReluBwdArgs {
+    int n_rows, n_groups;
+    ReluBwdGroup g[kMaxGroupsPerType];
+    const float *H;  // [P][n_rows][32]
+    float *dA;       // [P][n_rows][32]
+};
+
+struct DenseArgs {
+    // one group, layer 2.  H: [P1][n_j][32]; W2: [K][D1][D2] row-major; P2/G2: [K*n_j][D2]
+    const float *H, *W2;
+    float *P2;        // forward output
+    const float *G2;  // backward input
+    float *dW2;       // [K][D1*D2] (direct) or partial [K][n_chunks][D1*D2]
+    float *dHpart;    // [n_kchunks][P1][n_j][32]
+    const uint32_t *mask;  // [K*n_j*P1] words or null
+    float scale;
+    int K, n_j;
+    int rows_per_chunk, n_row_chunks;  // dW2 split over rows
+    int rel_per_chunk, n_kchunks;      // dH split over relations
+};
+
+struct DecodeArgs {
+    const float *Zi, *Zj;  // [n][32]
+    float *dZi, *dZj;
+    int n_i, n_j;
+    const int *batch;   // [B][2]
+    const long long *neg_in;  // [B] or null
+    long long *neg_out;       // [B]
+    const uint32_t *thr;      // sampler CDF of the row type for this relation, n_thr entries
+    int n_thr;
+    int B, decoder, loss_kind;
+    float margin, neg_weight;
+    const float *glb, *loc;   // decoder parameters of this relation (see decode.cu)
+    float *g_glb, *g_loc;     // their gradients
+    float *pos_out, *neg_score_out, *loss_out;
+    uint32_t seed_lo, seed_hi, step, relation;
+};
+
+struct PredictArgs {
+    const float *Zi, *Zj;
+    int n_i, n_j, decoder;
+    const float *glb;         // group-level parameter (dedicom R) or null
+    const float *loc;         // first relation's local parameter
+    long long loc_stride;     // floats between consecutive relations' local parameters
+    int count;
+    float *out;               // [count][n_i][n_j]
+};
+
+// ---------------------------------------------------------------- kernel launchers (host)
+void launch_spmm(const SpmmArgs &a, int P, cudaStream_t s);
+void launch_seg_reduce(const SpmmArgs &a, const int *multi_rows, int n_multi, int P, cudaStream_t s);
+void launch_spmm_staged(const StagedArgs &a, int rows_per_warp, cudaStream_t s);
+size_t staged_smem_bytes(int n_j);
+bool staged_supported(int n_i, int n_j, int K);
+void launch_node_epilogue(const EpiArgs &a, int P, cudaStream_t s);
+void launch_l2norm_bwd(const L2BwdArgs &a, int P, cudaStream_t s);
+void launch_relu_bwd(const ReluBwdArgs &a, int P, cudaStream_t s);
+void launch_gen_mask(uint32_t *words, long long n_words, long long bits_per_rel, int words_per_rel_or_0, int r0,
+                     uint32_t stream_id, uint32_t step, uint64_t seed, uint32_t threshold, cudaStream_t s);
+void launch_project(const DenseArgs &a, int D1, int D2, cudaStream_t s);
+void launch_dw2(const DenseArgs &a, int D1, int D2, cudaStream_t s);
+void launch_dw2_reduce(const float *part, float *out, int K, int n_chunks, int elems, cudaStream_t s);
+void launch_dh(const DenseArgs &a, int D1, int D2, cudaStream_t s);
+void launch_decode(const DecodeArgs &a, cudaStream_t s);
+void launch_predict(const PredictArgs &a, cudaStream_t s);
+void launch_predict_edges(const PredictArgs &a, const int *edges, int n_edges, int apply_sigmoid, float *out,
+                          cudaStream_t s);
+void launch_adam(float *p, const float *g, float *m, float *v, long long n, float alpha, float one_minus_b1,
+                 float one_minus_b2, float eps, cudaStream_t s);
+void launch_relation_matrices(int decoder, const float *glb, const float *loc, float *glb_out, float *loc_out,
+                              cudaStream_t s);
+
+}  // namespace dgn

@@ -1,0 +1,221 @@
+// Row-local pieces of the encoder and the optimizer update:
+//   node_epilogue_kernel -- ordered sum of the SpMM partials of every (i, j) group, l2-normalise
+//                           per group (tf.nn.l2_normalize, layers.py:93,117), sum over the groups of
+//                           a node type and optional ReLU (model.py:74-75 / :86-88)
+//   l2norm_bwd_kernel    -- its backward per group
+//   relu_bwd_kernel      -- ordered sum of the dH partials + ReLU mask
+//   gen_mask_kernel      -- Philox4x32-10 dropout keep-bits (layers.py:23-31, :112)
+//   adam_kernel          -- TF-1.8 ApplyAdam (optimizer.py:111-113)
+#include <algorithm>
+#include <type_traits>
+
+#include "dgn_internal.cuh"
+#include "philox.cuh"
+
+namespace dgn {
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
+    return x;
+}
+
+template <int P>
+__global__ void __launch_bounds__(256) node_epilogue_kernel(const EpiArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int row = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (row >= a.n_rows) return;
+    float total[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) total[p] = 0.f;
+    for (int gi = 0; gi < a.n_groups; ++gi) {
+        const EpiGroup &g = a.g[gi];
+        float s[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) s[p] = 0.f;
+        if (g.row_seg_ptr != nullptr) {
+            const int s0 = g.row_seg_ptr[row], s1 = g.row_seg_ptr[row + 1];
+            for (int sg = s0; sg < s1; ++sg)
+#pragma unroll
+                for (int p = 0; p < P; ++p) s[p] += g.partial[((size_t)sg * P + p) * 32 + lane];
+        } else {
+            for (int sl = 0; sl < g.n_slots; ++sl)
+#pragma unroll
+                for (int p = 0; p < P; ++p) s[p] += g.partial[(((size_t)sl * P + p) * a.n_rows + row) * 32 + lane];
+        }
+        float sq = 0.f;
+#pragma unroll
+        for (int p = 0; p < P; ++p) sq = fmaf(s[p], s[p], sq);
+        sq = warp_sum(sq);
+        const float nrm = sqrtf(fmaxf(sq, kL2Eps));
+        const float inv = 1.f / nrm;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const float y = s[p] * inv;
+            g.Y[((size_t)p * a.n_rows + row) * 32 + lane] = y;
+            total[p] += y;
+        }
+        if (lane == 0) g.nrm[row] = nrm;
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+        a.out[((size_t)p * a.n_rows + row) * 32 + lane] = a.relu ? fmaxf(total[p], 0.f) : total[p];
+}
+
+// y = s / n, n = sqrt(max(|s|^2, eps)):  ds = (dy - y (y . dy)) / n; clamped rows: ds = dy / n
+template <int P>
+__global__ void __launch_bounds__(256) l2norm_bwd_kernel(const L2BwdArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int row = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (row >= a.n_rows) return;
+    float y[P], dy[P], dot = 0.f;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const size_t o = ((size_t)p * a.n_rows + row) * 32 + lane;
+        y[p] = a.Y[o];
+        dy[p] = a.dY[o];
+        dot = fmaf(y[p], dy[p], dot);
+    }
+    dot = warp_sum(dot);
+    const float nrm = a.nrm[row];
+    if (nrm * nrm <= kL2Eps * 1.0000001f) dot = 0.f;  // clamp active: y = s * rsqrt(eps) is linear in s
+    const float inv = 1.f / nrm;
+#pragma unroll
+    for (int p = 0; p < P; ++p) a.dS[((size_t)p * a.n_rows + row) * 32 + lane] = (dy[p] - y[p] * dot) * inv;
+}
+
+template <int P>
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const ReluBwdArgs a) {
+    const size_t n = (size_t)P * a.n_rows * 32;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int gi = 0; gi < a.n_groups; ++gi)
+            for (int c = 0; c < a.g[gi].n_chunks; ++c) s += a.g[gi].part[(size_t)c * n + i];
+        a.dA[i] = a.H[i] > 0.f ? s : 0.f;
+    }
+}
+
+// One thread per output word.  Bit b of relation `rel` is element e = b of that relation's
+// stream: word (e & 3) of Philox(counter = (e >> 2, relation, stream, step), key = seed).
+// words_per_rel == 0: relations are packed back to back at bit granularity (layer 1, bit index
+// = rel * bits_per_rel + e); otherwise each relation owns words_per_rel whole words (layer 2).
+__global__ void gen_mask_kernel(uint32_t *__restrict__ words, long long n_words, long long bits_per_rel,
+                                int words_per_rel, int r0, uint32_t stream_id, uint32_t step, uint32_t seed_lo,
+                                uint32_t seed_hi, uint32_t threshold, long long total_bits) {
+    const long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    uint32_t out = 0;
+    long long cached_rel = -1, cached_ctr = -1;
+    uint4 rnd = make_uint4(0, 0, 0, 0);
+    for (int b = 0; b < 32; ++b) {
+        long long rel, e;
+        if (words_per_rel > 0) {
+            rel = w / words_per_rel;
+            e = (w % words_per_rel) * 32 + b;
+            if (e >= bits_per_rel) break;
+        } else {
+            const long long bit = w * 32 + b;
+            if (bit >= total_bits) break;
+            rel = bit / bits_per_rel;
+            e = bit % bits_per_rel;
+        }
+        const long long ctr = e >> 2;
+        if (rel != cached_rel || ctr != cached_ctr) {
+            rnd = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(r0 + rel), stream_id, step),
+                                make_uint2(seed_lo, seed_hi));
+            cached_rel = rel;
+            cached_ctr = ctr;
+        }
+        const uint32_t u = (e & 3) == 0 ? rnd.x : (e & 3) == 1 ? rnd.y : (e & 3) == 2 ? rnd.z : rnd.w;
+        if (u >= threshold) out |= 1u << b;
+    }
+    words[w] = out;
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float *__restrict__ p, const float *__restrict__ g,
+                                                   float *__restrict__ m, float *__restrict__ v, long long n,
+                                                   float alpha, float omb1, float omb2, float eps) {
+    const long long n4 = n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 P4 = reinterpret_cast<float4 *>(p)[i], G4 = reinterpret_cast<const float4 *>(g)[i];
+        float4 M4 = reinterpret_cast<float4 *>(m)[i], V4 = reinterpret_cast<float4 *>(v)[i];
+        float *pp = &P4.x, *gg = &G4.x, *mm = &M4.x, *vv = &V4.x;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            mm[q] += (gg[q] - mm[q]) * omb1;
+            vv[q] += (gg[q] * gg[q] - vv[q]) * omb2;
+            pp[q] -= (mm[q] * alpha) / (sqrtf(vv[q]) + eps);
+        }
+        reinterpret_cast<float4 *>(p)[i] = P4;
+        reinterpret_cast<float4 *>(m)[i] = M4;
+        reinterpret_cast<float4 *>(v)[i] = V4;
+    }
+    for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+        float mi = m[i], vi = v[i];
+        const float gi = g[i];
+        mi += (gi - mi) * omb1;
+        vi += (gi * gi - vi) * omb2;
+        p[i] -= (mi * alpha) / (sqrtf(vi) + eps);
+        m[i] = mi;
+        v[i] = vi;
+    }
+}
+
+template <typename F>
+void dispatch_panels(int P, F &&f) {
+    switch (P) {
+        case 1: f(std::integral_constant<int, 1>{}); break;
+        case 2: f(std::integral_constant<int, 2>{}); break;
+        case 4: f(std::integral_constant<int, 4>{}); break;
+        default: DGN_FAIL(DGN_ERR_UNSUPPORTED, "%d panels (hidden sizes must be 32, 64 or 128)", P);
+    }
+}
+
+}  // namespace
+
+void launch_node_epilogue(const EpiArgs &a, int P, cudaStream_t s) {
+    if (a.n_rows == 0) return;
+    dim3 grid((unsigned)((a.n_rows + 7) / 8)), block(256);
+    dispatch_panels(P, [&](auto tag) { node_epilogue_kernel<decltype(tag)::value><<<grid, block, 0, s>>>(a); });
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_l2norm_bwd(const L2BwdArgs &a, int P, cudaStream_t s) {
+    if (a.n_rows == 0) return;
+    dim3 grid((unsigned)((a.n_rows + 7) / 8)), block(256);
+    dispatch_panels(P, [&](auto tag) { l2norm_bwd_kernel<decltype(tag)::value><<<grid, block, 0, s>>>(a); });
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_relu_bwd(const ReluBwdArgs &a, int P, cudaStream_t s) {
+    if (a.n_rows == 0) return;
+    const size_t n = (size_t)P * a.n_rows * 32;
+    dim3 grid((unsigned)std::min<size_t>((n + 255) / 256, 148 * 8)), block(256);
+    dispatch_panels(P, [&](auto tag) { relu_bwd_kernel<decltype(tag)::value><<<grid, block, 0, s>>>(a); });
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_gen_mask(uint32_t *words, long long n_words, long long bits_per_rel, int words_per_rel, int r0,
+                     uint32_t stream_id, uint32_t step, uint64_t seed, uint32_t threshold, cudaStream_t s) {
+    if (n_words == 0) return;
+    const long long total_bits = n_words * 32;  // packed mode: caller rounds the word count up
+    dim3 grid((unsigned)((n_words + 255) / 256)), block(256);
+    gen_mask_kernel<<<grid, block, 0, s>>>(words, n_words, bits_per_rel, words_per_rel, r0, stream_id, step,
+                                           (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), threshold,
+                                           total_bits);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_adam(float *p, const float *g, float *m, float *v, long long n, float alpha, float omb1, float omb2,
+                 float eps, cudaStream_t s) {
+    if (n == 0) return;
+    dim3 grid(148 * 8), block(256);
+    adam_kernel<<<grid, block, 0, s>>>(p, g, m, v, n, alpha, omb1, omb2, eps);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace dgn

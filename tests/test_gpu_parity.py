@@ -1,0 +1,229 @@
+"""Parity of the CUDA path (through the C ABI, via decagon_b200.engine) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): indices bit-exact; embeddings, logits, losses and
+gradients within rel-err 1e-5 of the float64 oracle, where rel-err = max|a-b| / max|b|.
+"""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import common
+from common import Case, rel_err
+from decagon_b200 import _lib, datasets
+from oracle import decagon_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+SEED = 42
+
+
+@pytest.fixture(scope='module')
+def toy():
+    c = Case(datasets.toy_graph())
+    c.eng = c.engine()
+    return c
+
+
+@pytest.fixture(scope='module')
+def toy_mixed():
+    c = Case(datasets.toy_graph(common.MIXED_DECODERS))
+    c.eng = c.engine()
+    return c
+
+
+@pytest.fixture(scope='module')
+def mini():
+    c = Case(common.mini_poly(), batch_size=64)
+    c.eng = c.engine()
+    return c
+
+
+def check_forward(c, eng, rate, step):
+    masks = O.masks_for(c.graph, rate, step, SEED)
+    Z, cache = O.encoder_forward(c.graph, c.p64, rate, masks)
+    eng.forward(rate, SEED, step)
+    for t in Z:
+        assert rel_err(eng.hidden1_of(t), cache['H'][t]) <= TOL, ('hidden1', t)
+        assert rel_err(eng.embeddings(t), Z[t]) <= TOL, ('embeddings', t)
+    for gi, g in enumerate(c.graph.groups):
+        assert rel_err(eng.tensor(_lib.TENSOR_LAYER1_GROUP, gi), cache['Y1'][g]) <= TOL, ('layer1', g)
+        assert rel_err(eng.tensor(_lib.TENSOR_LAYER2_GROUP, gi), cache['Y2'][g]) <= TOL, ('layer2', g)
+    return Z
+
+
+def check_grads(c, eng, r, batch, rate, step, loss_kind, negs=None):
+    g, k = c.graph.flat[r]
+    if negs is None:
+        negs = O.sample_negatives(c.thresholds(r), len(batch), r, step, SEED)
+    masks = O.masks_for(c.graph, rate, step, SEED)
+    loss, pos, neg, grads, Z = O.train_step_grads(c.graph, c.p64, g, k, batch, negs, rate, masks, loss_kind)
+    got = eng.train_step(r, batch, negatives=negs, loss=loss_kind, dropout=rate, seed=SEED, step=step,
+                         apply_update=False)
+    gpos, gneg, gsamples = eng.last_batch_outputs(len(batch))
+    assert np.array_equal(gsamples, negs)
+    assert rel_err(gpos, pos) <= TOL and rel_err(gneg, neg) <= TOL
+    assert abs(float(got) - loss) <= TOL * max(abs(loss), 1.0), (float(got), loss)
+    eg = eng.get_grads()
+    for name in grads:
+        for gg in grads[name]:
+            assert rel_err(eg[name][gg], grads[name][gg]) <= TOL, (name, gg, rel_err(eg[name][gg], grads[name][gg]))
+
+
+def test_csr_bit_exact(toy):
+    """Device CSR == scipy's canonical CSR of the reference tuple (indices bit-exact, values =
+    float32 cast of the float64 normalisation)."""
+    for r, (g, k) in enumerate(toy.graph.flat):
+        coords, values, shape = toy.it.adj_train[g][k]
+        ref = sp.csr_matrix((np.asarray(values).astype(np.float32), (coords[:, 0], coords[:, 1])), shape=shape)
+        ref.sort_indices()
+        rowptr, col, val = toy.eng.get_csr(r)
+        assert np.array_equal(rowptr, ref.indptr) and np.array_equal(col, ref.indices)
+        assert np.array_equal(val, ref.data)
+
+
+@pytest.mark.parametrize('rate', [0.0, 0.1])
+def test_forward_toy(toy, rate):
+    check_forward(toy, toy.eng, rate, step=3)
+
+
+@pytest.mark.parametrize('rate', [0.0, 0.1])
+def test_forward_mini_staged(mini, rate):
+    check_forward(mini, mini.eng, rate, step=1)
+
+
+@pytest.mark.parametrize('loss_kind', ['hinge', 'xent'])
+@pytest.mark.parametrize('rate', [0.0, 0.1])
+def test_train_step_grads_toy(toy, loss_kind, rate):
+    for step, (r, batch) in enumerate(toy.batches(4)):
+        check_grads(toy, toy.eng, r, batch, rate, step, loss_kind)
+
+
+@pytest.mark.parametrize('loss_kind', ['hinge', 'xent'])
+def test_train_step_grads_all_decoders(toy_mixed, loss_kind):
+    for step, (r, batch) in enumerate(toy_mixed.batches(4)):
+        check_grads(toy_mixed, toy_mixed.eng, r, batch, 0.1, step, loss_kind)
+
+
+@pytest.mark.parametrize('kind', ['innerproduct', 'distmult', 'bilinear', 'dedicom'])
+def test_each_decoder_everywhere(kind):
+    """Config #2: every group set to the same decoder kind."""
+    c = Case(datasets.toy_graph({g: kind for g in datasets.DEFAULT_DECODERS}))
+    eng = c.engine()
+    for step, (r, batch) in enumerate(c.batches(4)):
+        check_grads(c, eng, r, batch, 0.0, step, 'hinge')
+    eng.close()
+
+
+def test_train_step_grads_mini_staged(mini):
+    for step, (r, batch) in enumerate(mini.batches(8)):
+        check_grads(mini, mini.eng, r, batch, 0.1, step, 'hinge')
+
+
+def test_staged_matches_gather():
+    """The staged (shared-memory) SpMM and the gather SpMM are two code paths for one result."""
+    c = Case(common.mini_poly(seed=3), batch_size=64)
+    os.environ['DGN_DISABLE_STAGED'] = '1'
+    try:
+        gather = c.engine()
+    finally:
+        del os.environ['DGN_DISABLE_STAGED']
+    staged = c.engine()
+    for eng in (gather, staged):
+        eng.forward(0.1, SEED, 0)
+    for t in c.graph.n_nodes:
+        assert rel_err(staged.embeddings(t), gather.embeddings(t)) <= TOL
+    check_forward(c, gather, 0.1, 0)
+    r, batch = c.batches(1)[0]
+    check_grads(c, gather, r, batch, 0.1, 0, 'hinge')
+    gather.close()
+    staged.close()
+
+
+def test_negative_sampler_bit_exact(toy):
+    for step, (r, batch) in enumerate(toy.batches(6)):
+        toy.eng.train_step(r, batch, negatives=None, seed=SEED, step=step, apply_update=False)
+        _, _, samples = toy.eng.last_batch_outputs(len(batch))
+        assert np.array_equal(samples, O.sample_negatives(toy.thresholds(r), len(batch), r, step, SEED))
+
+
+def test_adam_update_tf1():
+    """Five optimizer steps: the parameters must follow TF-1.8 ApplyAdam applied to the
+    gradients the device itself produced (isolates the update rule and the beta-power
+    schedule); every variable moves, also those with zero gradient."""
+    c = Case(datasets.toy_graph())
+    eng = c.engine()
+    eng.reset_optimizer()
+    p = O.cast_params(eng.get_params(), np.float32)
+    adam = O.AdamTF1(p, lr=1e-3)
+    for step, (r, batch) in enumerate(c.batches(5)):
+        eng.train_step(r, batch, negatives=None, seed=SEED, step=step, dropout=0.1, apply_update=True)
+        grads = eng.get_grads()
+        adam.apply(p, grads)
+        now = eng.get_params()
+        for name in p:
+            for g in p[name]:
+                assert np.abs(now[name][g] - p[name][g]).max() <= 2e-7, (step, name, g)
+    eng.close()
+
+
+def test_multi_step_training_matches_oracle():
+    """Ten full training steps (forward, decode, backward, Adam) on both sides with identical
+    batches, negatives and dropout masks: losses agree within 1e-4 and the loss goes down."""
+    c = Case(datasets.toy_graph())
+    eng = c.engine()
+    eng.reset_optimizer()
+    p = O.cast_params(c.p32, np.float64)
+    adam = O.AdamTF1(p, lr=1e-3)
+    losses_dev, losses_ref = [], []
+    for step, (r, batch) in enumerate(c.batches(10)):
+        g, k = c.graph.flat[r]
+        negs = O.sample_negatives(c.thresholds(r), len(batch), r, step, SEED)
+        masks = O.masks_for(c.graph, 0.1, step, SEED)
+        loss, _, _, grads, _ = O.train_step_grads(c.graph, p, g, k, batch, negs, 0.1, masks, 'hinge')
+        adam.apply(p, grads)
+        losses_ref.append(loss)
+        losses_dev.append(float(eng.train_step(r, batch, negatives=None, seed=SEED, step=step, dropout=0.1)))
+    assert rel_err(losses_dev, losses_ref) <= 1e-4, (losses_dev, losses_ref)
+    eng.close()
+
+
+def test_predictions(toy_mixed):
+    """optimizer.predictions for one relation of every decoder kind + sampled sigmoid scores."""
+    c, eng = toy_mixed, toy_mixed.eng
+    Z = check_forward(c, eng, 0.0, 0)
+    rng = np.random.RandomState(0)
+    for r, (g, k) in enumerate(c.graph.flat):
+        ref = O.predict_all_pairs(c.graph, c.p64, Z, g, k)
+        assert rel_err(eng.predict(r), ref) <= TOL, (g, k)
+        edges = np.stack([rng.randint(0, ref.shape[0], 200), rng.randint(0, ref.shape[1], 200)], axis=1)
+        assert rel_err(eng.predict_edges(r, edges), O.sampled_scores(ref, edges)) <= TOL
+        glb, loc = O.relation_matrices(c.graph, c.p64, g, k)
+        eglb, eloc = eng.relation_matrices(r)
+        assert rel_err(eglb, glb) <= 1e-7 and rel_err(eloc, loc) <= 1e-7
+
+
+def test_param_roundtrip_and_errors(toy):
+    eng = toy.eng
+    back = eng.get_params()
+    for name in toy.p32:
+        for g in toy.p32[name]:
+            assert np.array_equal(back[name][g], toy.p32[name][g])
+    with pytest.raises(ValueError):
+        eng.train_step(0, np.array([[0, 10 ** 6]], dtype=np.int32))
+    with pytest.raises(ValueError):
+        eng.train_step(10 ** 4, np.zeros((4, 2), dtype=np.int32))
+    with pytest.raises(ValueError):
+        eng.set_param(_lib.PARAM_W2, (0, 0), 0, np.zeros((3, 3), dtype=np.float32))
+
+
+def test_hidden_sizes():
+    """hidden1 = 32 and 128 exercise the 1- and 4-panel kernels."""
+    for h1 in (32, 128):
+        c = Case(common.mini_poly(n_types=10, seed=h1), batch_size=64, hidden1=h1)
+        eng = c.engine()
+        check_forward(c, eng, 0.1, 0)
+        r, batch = c.batches(1)[0]
+        check_grads(c, eng, r, batch, 0.1, 0, 'hinge')
+        eng.close()
