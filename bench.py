@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Headline benchmark: full-batch training steps on the polypharmacy-shape graph (BASELINE.json
+config #3) -- 19 085 proteins, 645 drugs, 964 side-effect types (1932 relation matrices with
+transposed twins), hidden 64/32, batch 512, dropout 0.1, hinge loss, TF1 Adam.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one reference ``session.run([opt_op, cost, batch_edge_type_idx])``
+(``main/Trainer/DecagonTrainer.py:94-100``): encoder forward over the whole graph, 512-edge
+decode of one relation, full backward, Adam on all ~87 M parameters.  Prints ONE JSON line
+(contract in the task statement).  ``oracle/`` is touched only for the CPU baseline legs.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 3  # dropout / negative-sampler streams of the throughput runs
+HYPER = dict(hidden1=64, hidden2=32, batch_size=512, dropout=0.1, lr=1e-3, margin=0.1, val_test_size=0.05)
+PLACEHOLDERS = {k: k for k in ['batch', 'batch_edge_type_idx', 'batch_row_edge_type', 'batch_col_edge_type', 'dropout']}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------- workload
+def build_workload(config, scale):
+    from decagon_b200 import datasets
+    from decagon_b200.deep.minibatch import EdgeMinibatchIterator
+    t0 = time.time()
+    if config == 'toy':
+        inputs = datasets.toy_graph()
+    else:
+        inputs = datasets.polypharmacy_graph(scale=scale)
+    np.random.seed(0)
+    it = EdgeMinibatchIterator(inputs.adj_mats, inputs.feat, inputs.edge_types, {}, batch_size=HYPER['batch_size'],
+                               val_test_size=HYPER['val_test_size'])
+    log('workload built in %.1fs' % (time.time() - t0))
+    return inputs, it
+
+
+def steps_per_epoch(it):
+    """Length of one reference epoch (``while not iterator.end()``, DecagonTrainer.py:54):
+    4 * (sum of full batches of the side-effect relations and of the PPI twin) + O(1), SURVEY.md a3."""
+    B = it.batch_size
+    free = sum(len(it.train_edges[1, 1][k]) // B for k in range(it.edge_types[1, 1]))
+    if it.edge_types[0, 0] > 1:
+        free += len(it.train_edges[0, 0][1]) // B
+    return 4 * free + 4
+
+
+def glorot_params(inputs, hidden1, hidden2, seed=1):
+    rng = np.random.RandomState(seed)
+
+    def glorot(shape, fan_in, fan_out):
+        a = np.sqrt(6.0 / (fan_in + fan_out))
+        return rng.uniform(-a, a, size=shape).astype(np.float32)
+
+    p = {'W1': {}, 'W2': {}, 'R': {}, 'D': {}}
+    for g, K in inputs.edge_types.items():
+        F = inputs.num_feat[g[1]]
+        p['W1'][g] = glorot((K, F, hidden1), F, hidden1)
+        p['W2'][g] = glorot((K, hidden1, hidden2), hidden1, hidden2)
+        kind = inputs.edge_type2decoder[g]
+        if kind == 'dedicom':
+            p['R'][g] = glorot((hidden2, hidden2), hidden2, hidden2)
+        if kind in ('dedicom', 'distmult'):
+            p['D'][g] = glorot((K, hidden2), hidden2, 1)
+        elif kind == 'bilinear':
+            p['D'][g] = glorot((K, hidden2, hidden2), hidden2, hidden2)
+    return p
+
+
+def next_batch(it):
+    fd = it.next_minibatch_feed_dict(PLACEHOLDERS)
+    return int(fd['batch_edge_type_idx']), np.ascontiguousarray(fd['batch'], dtype=np.int32)
+
+
+def algorithmic_bytes(inputs, it, hidden1, hidden2):
+    """fp32 values, int32 indices, CSR, dense operand counted once per relation,
+    no cache credit.  Returns {phase: bytes per launch}."""
+    out = {}
+    for gi, (g, K) in enumerate(inputs.edge_types.items()):
+        n_i, n_j = inputs.n_nodes[g[0]], inputs.n_nodes[g[1]]
+        nnz = sum(len(it.adj_train[g][k][1]) for k in range(K))
+        csr = nnz * 8 + K * (n_i + 1) * 4
+        csr_t = nnz * 8 + K * (n_j + 1) * 4
+        out['spmm_fwd1/g%d' % gi] = csr + K * n_j * hidden1 * 4 + n_i * hidden1 * 4
+        out['spmm_fwd2/g%d' % gi] = csr + K * hidden1 * hidden2 * 4 + n_j * hidden1 * 4 + n_i * hidden2 * 4
+        out['spmm_bwd2/g%d' % gi] = csr_t + n_i * hidden2 * 4 + K * hidden1 * hidden2 * 4 + n_j * hidden1 * 4
+        out['spmm_bwd1/g%d' % gi] = csr_t + n_i * hidden1 * 4 + K * n_j * hidden1 * 4
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([x.strip() for x in out.strip().split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        good = [s for s in self.samples if len(s) == 6 and s[0].isdigit()]
+        if not good:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i] == 'Active' for s in good)]
+        return {'sm_mhz': float(np.median([int(s[0]) for s in good])), 'sm_max_mhz': float(good[0][1]), 'reasons': reasons,
+                'samples': len(good)}
+
+
+# ----------------------------------------------------------------------------- CPU legs
+def cpu_port_steps(inputs, it, params, n_steps, n_warmup, budget_s=150.0):
+    """The reference-style torch-CPU port (oracle/torch_ref.py): FULL train steps (all relation
+    matrices, forward + backward + Adam), float32, all host threads.  A full step takes ~10 s at
+    the polypharmacy shape, so the number of timed steps is bounded by a time budget:
+    n = min(n_steps, budget / warm-up step time).  Returns (seconds per step, n timed, text)."""
+    import torch
+    from oracle import decagon_oracle as O
+    from oracle.torch_ref import TorchDecagon
+    torch.set_num_threads(os.cpu_count())
+    graph = O.Graph.from_iterator(it, inputs.edge_type2decoder, HYPER['hidden1'], HYPER['hidden2'], dtype=np.float32)
+    model = TorchDecagon(graph, params, torch.float32, lr=HYPER['lr'])
+    rng = np.random.RandomState(2)
+    masks = None
+
+    def one(step):
+        g = [(0, 0), (0, 1), (1, 0), (1, 1)][step % 4]
+        edges = it.train_edges[g][0]
+        batch = edges[rng.randint(0, len(edges), HYPER['batch_size'])]
+        negs = rng.randint(0, graph.n_nodes[g[0]], HYPER['batch_size'])
+        t0 = time.perf_counter()
+        model.train_step(g, 0, batch, negs, rate=0.0, masks=masks, margin=HYPER['margin'])
+        return time.perf_counter() - t0
+
+    warm = [one(s) for s in range(n_warmup)]
+    n = int(max(1, min(n_steps, budget_s / max(warm[-1], 1e-9))))
+    times = [one(n_warmup + s) for s in range(n)]
+    text = ('%d full train steps (all %d relation matrices; %d requested, bounded by a %.0f s budget) after %d warm-up, '
+            'torch-CPU float32 port of the TF graph (oracle/torch_ref.py), dropout masks not drawn'
+            % (n, sum(inputs.edge_types.values()), n_steps, budget_s, n_warmup))
+    return float(np.mean(times)), n, text
+
+
+# ----------------------------------------------------------------------------- main legs
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    inputs, it = build_workload(args.config, args.scale)
+    params = glorot_params(inputs, HYPER['hidden1'], HYPER['hidden2'])
+    sec, n_timed, sample = cpu_port_steps(inputs, it, params, args.steps, 1, args.reference_budget)
+    spe = steps_per_epoch(it)
+    value = 1.0 / sec / spe
+    line = {
+        'impl': 'reference', 'metric': 'train_epochs_per_s', 'value': value, 'unit': 'epochs/s', 'n_gpus': args.gpus,
+        'steps': n_timed, 'warmup': 1, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'steps_per_s': 1.0 / sec, 'steps_per_epoch': spe,
+        'config': workload_config(args, inputs),
+        'cpu_baseline': {'value': value, 'unit': 'epochs/s', 'cores': os.cpu_count(), 'kind': 'port',
+                         'sample': sample, 'steps_per_s': 1.0 / sec},
+        'e2e': {'value': value, 'unit': 'epochs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, inputs):
+    return {'workload': 'polypharmacy-shape synthetic (BASELINE config #3)' if args.config == 'poly' else 'toy (config #1)',
+            'n_proteins': inputs.n_nodes[0], 'n_drugs': inputs.n_nodes[1],
+            'relation_matrices': sum(inputs.edge_types.values()), 'hidden': [HYPER['hidden1'], HYPER['hidden2']],
+            'batch': HYPER['batch_size'], 'dropout': HYPER['dropout'], 'loss': 'hinge', 'optimizer': 'adam(tf1)',
+            'scale': args.scale, 'l2': 'per-step working set (>4 GB) exceeds the 126 MB L2; no explicit flush'}
+
+
+def run_ours(args):
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    from decagon_b200.engine import Engine
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group('nccl')
+
+    inputs, it = build_workload(args.config, args.scale)
+    t0 = time.time()
+    eng = Engine(inputs.n_nodes, inputs.num_feat, inputs.edge_types, inputs.edge_type2decoder, HYPER['hidden1'],
+                 HYPER['hidden2'], device=local_rank)
+    eng.load_iterator(it, inputs.degrees)
+    eng.set_params(glorot_params(inputs, HYPER['hidden1'], HYPER['hidden2']))
+    eng.reset_optimizer()
+    log('engine loaded in %.1fs, %d parameters' % (time.time() - t0, eng.n_params()))
+
+    np.random.seed(2)
+    it.shuffle()
+    kw = dict(loss='hinge', margin=HYPER['margin'], lr=HYPER['lr'], dropout=HYPER['dropout'], seed=SEED)
+    step = 0
+    for _ in range(max(args.warmup, 3)):
+        r, batch = next_batch(it)
+        eng.train_step(r, batch, step=step, **kw)
+        step += 1
+
+    def barrier():
+        eng.sync()
+        if dist is not None:
+            dist.barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # (1) device-resident throughput: graph, parameters and optimizer state live in HBM; the only
+    # per-step input is the 4 KB batch index block; CUDA events on the library's stream
+    batches = [next_batch(it) for _ in range(args.steps)]
+    barrier()
+    eng.timing_reset()
+    eng.timer_start()
+    for r, batch in batches:
+        eng.train_step(r, batch, step=step, want_loss=False, **kw)
+        step += 1
+    dev_ms = eng.timer_stop()
+    launches = eng.launch_count()
+    barrier()
+
+    # (2) end to end through the public call with host buffers: host iterator, H2D of the batch,
+    # the step, D2H of the loss, every step
+    barrier()
+    t0 = time.perf_counter()
+    losses = []
+    for _ in range(args.steps):
+        r, batch = next_batch(it)
+        losses.append(eng.train_step(r, batch, step=step, want_loss=True, **kw))
+        step += 1
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.summary()
+
+    # (3) per-kernel times (CUDA events per phase) for the roofline
+    eng.timing(True)
+    eng.timing_reset()
+    n_prof = min(args.steps, 10)
+    for r, batch in batches[:n_prof]:
+        eng.train_step(r, batch, step=step, want_loss=False, **kw)
+        step += 1
+    eng.sync()
+    alg = algorithmic_bytes(inputs, it, HYPER['hidden1'], HYPER['hidden2'])
+    phases = {}
+    names = list(alg) + ['project', 'dw2', 'dh', 'mask', 'epilogue', 'decode', 'adam']
+    for name in names:
+        ms, n = eng.timing_get(name)
+        if n:
+            phases[name] = {'ms_per_step': ms / n_prof}
+            if name in alg:
+                phases[name]['bytes'] = alg[name]
+                phases[name]['gbs'] = alg[name] / (ms / n_prof * 1e-3) / 1e9
+    eng.timing(False)
+
+    if dist is not None:
+        import torch
+        t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s = float(t[0]), float(t[1])
+    if rank != 0:
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = peaks.get('hbm_gbs', 6650.0)
+    peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s (B200_PROFILING.md)'
+    spmm = {k: v for k, v in phases.items() if k.startswith('spmm_fwd')}
+    top = max(spmm, key=lambda k: spmm[k]['ms_per_step'])
+    spe = steps_per_epoch(it)
+    sps = args.steps / (dev_ms * 1e-3)
+    e2e_sps = args.steps / e2e_s
+    line = {
+        'metric': 'train_epochs_per_s', 'value': sps / spe, 'unit': 'epochs/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'steps_per_s': sps, 'steps_per_epoch': spe,
+        'config': workload_config(args, inputs),
+        'clocks': clocks,
+        'e2e': {'value': e2e_sps / spe, 'unit': 'epochs/s', 'steps_per_s': e2e_sps,
+                'h2d_bytes_per_step': HYPER['batch_size'] * 2 * 4, 'd2h_bytes_per_step': 4},
+        'gpu_launches': int(launches),
+        'roofline': {'bound': 'hbm', 'kernel': top, 'achieved': spmm[top]['gbs'], 'peak': peak, 'unit': 'GB/s',
+                     'frac': spmm[top]['gbs'] / peak, 'traffic': None, 'peak_source': peak_src,
+                     'algorithmic_bytes': spmm[top]['bytes'], 'ms': spmm[top]['ms_per_step']},
+        'kernels': phases,
+        'loss_first_last': [float(losses[0]), float(losses[-1])],
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        sec, _, sample = cpu_port_steps(inputs, it, glorot_params(inputs, HYPER['hidden1'], HYPER['hidden2']), 2, 1, 25.0)
+        line['cpu_baseline'] = {'value': 1.0 / sec / spe, 'unit': 'epochs/s', 'steps_per_s': 1.0 / sec,
+                                'cores': os.cpu_count(), 'kind': 'port',
+                                'sample': sample}
+    print(json.dumps(line), flush=True)
+    eng.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default='poly', choices=['poly', 'toy'])
+    ap.add_argument('--scale', type=int, default=1)
+    ap.add_argument('--reference-budget', type=float, default=150.0, help='seconds of timed CPU steps')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()
