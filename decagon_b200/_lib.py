@@ -56,6 +56,7 @@ SIGNATURES = {
     'dgn_predict_relations_dev': (ctypes.c_int, [c_graph, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     'dgn_predict_edges': (ctypes.c_int, [c_graph, ctypes.c_int, c_i32p, ctypes.c_int32, ctypes.c_int, c_f32p]),
     'dgn_tensor_get': (ctypes.c_int, [c_graph, ctypes.c_int, ctypes.c_int, c_f32p, ctypes.c_int64]),
+    'dgn_tensor_set': (ctypes.c_int, [c_graph, ctypes.c_int, ctypes.c_int, c_f32p, ctypes.c_int64]),
     'dgn_relation_matrices': (ctypes.c_int, [c_graph, ctypes.c_int, c_f32p, c_f32p]),
     'dgn_sync': (ctypes.c_int, [c_graph]),
     'dgn_timing_enable': (ctypes.c_int, [c_graph, ctypes.c_int]),

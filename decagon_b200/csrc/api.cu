@@ -1116,6 +1116,19 @@ extern "C" int dgn_tensor_get(dgn_graph *g, int which, int index, float *out, in
     DGN_API_END
 }
 
+extern "C" int dgn_tensor_set(dgn_graph *g, int which, int index, const float *values, int64_t n) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(g && values, "null argument");
+    DGN_REQUIRE(which == DGN_TENSOR_EMBEDDINGS, "only the embeddings can be set (tensor id %d)", which);
+    DGN_REQUIRE(index >= 0 && index < g->n_types, "node type %d out of range", index);
+    NodeType &T = g->types[index];
+    DGN_REQUIRE(n == (int64_t)T.n * g->d2, "embeddings[%d]: got %lld floats, need %lld", index, (long long)n, (long long)T.n * g->d2);
+    CUDA_CHECK(cudaSetDevice(g->device));
+    CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    CUDA_CHECK(cudaMemcpy(T.Z, values, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));  // hidden2 == 32: one panel
+    DGN_API_END
+}
+
 extern "C" int dgn_relation_matrices(dgn_graph *g, int r, float *glb_out, float *loc_out) {
     DGN_API_BEGIN
     DGN_REQUIRE(g && glb_out && loc_out, "null argument");

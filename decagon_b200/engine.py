@@ -229,6 +229,10 @@ class Engine(object):
         check(self.lib.dgn_tensor_get(self._h, which, int(index), ptr(out, ctypes.c_float), out.size))
         return out
 
+    def set_embeddings(self, t, values):
+        arr = as_f32(values)
+        check(self.lib.dgn_tensor_set(self._h, _lib.TENSOR_EMBEDDINGS, int(t), ptr(arr, ctypes.c_float), arr.size))
+
     def embeddings(self, t):
         return self.tensor(_lib.TENSOR_EMBEDDINGS, t)
 

@@ -153,6 +153,11 @@ int dgn_predict_edges(dgn_graph *g, int r, const int32_t *edges, int32_t n_edges
 /* model.embeddings[t], model.hidden1[t], per-group layer outputs (DecagonLogger.py:239-242) */
 int dgn_tensor_get(dgn_graph *g, int which, int index, float *out, int64_t n);
 
+/* Load saved embeddings (the .npy dump of DecagonLogger.py:232-248) so that the predict calls can
+ * score them without running the encoder -- the use case of main/Predictor/NpPredictor.py:293-313.
+ * Only DGN_TENSOR_EMBEDDINGS can be set. */
+int dgn_tensor_set(dgn_graph *g, int which, int index, const float *values, int64_t n);
+
 /* latent_inters[r] / latent_varies[r] (model.py:116-137) as dense [hidden2, hidden2] */
 int dgn_relation_matrices(dgn_graph *g, int r, float *glb_out, float *loc_out);
 
