@@ -290,11 +290,12 @@ void build_group(dgn_graph *g, Group &G) {
 
     G.staged = g->allow_staged && staged_supported(n_i, n_j, K) && G.F_j == n_j;
     const long long target_warps = (long long)g->n_sm * 64 * 2;
-    int seg_len = (int)std::min<long long>(2048, std::max<long long>(64, (G.nnz / target_warps + 31) / 32 * 32));
+    // one quarter-warp per segment: aim at ~2 waves of quarter-warps, 32..2048 non-zeros each
+    int seg_len = (int)std::min<long long>(2048, std::max<long long>(32, (G.nnz / (4 * target_warps) + 31) / 32 * 32));
     G.fwd = upload_csr(fwd);
     G.fwd_seg = build_segments(fwd, seg_len, false);
     G.bwd = upload_csr(bwd);
-    G.bwd_seg = build_segments(bwd, 256, true);
+    G.bwd_seg = build_segments(bwd, std::min(256, std::max(32, seg_len)), true);
     if (!G.bwd_seg.trivial) G.bwd_partial = dev_alloc<float>(panel_floats(P1, G.bwd_seg.n_seg));
 
     if (G.staged) {
@@ -362,7 +363,7 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step) {
             a.op = op, a.P = P;
             a.slot_ptr = slots.ptr, a.slot_rel = slots.rel, a.n_slots = slots.n_slots;
             a.partial = part, a.mask = mask, a.scale = scale;
-            launch_spmm_staged(a, (G.n_i + 31) / 32, s);
+            launch_spmm_staged(a, s);
         } else {
             SpmmArgs a = {};
             a.rowptr = G.fwd.rowptr, a.col = G.fwd.col, a.val = G.fwd.val;

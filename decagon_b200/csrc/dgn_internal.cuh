@@ -182,7 +182,7 @@ struct PredictArgs {
 // ---------------------------------------------------------------- kernel launchers (host)
 void launch_spmm(const SpmmArgs &a, int P, cudaStream_t s);
 void launch_seg_reduce(const SpmmArgs &a, const int *multi_rows, int n_multi, int P, cudaStream_t s);
-void launch_spmm_staged(const StagedArgs &a, int rows_per_warp, cudaStream_t s);
+void launch_spmm_staged(const StagedArgs &a, cudaStream_t s);
 size_t staged_smem_bytes(int n_j);
 bool staged_supported(int n_i, int n_j, int K);
 void launch_node_epilogue(const EpiArgs &a, int P, cudaStream_t s);

@@ -108,24 +108,33 @@ __global__ void gen_mask_kernel(uint32_t *__restrict__ words, long long n_words,
     const long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (w >= n_words) return;
     uint32_t out = 0;
+    const uint2 key = make_uint2(seed_lo, seed_hi);
+    if (words_per_rel > 0) {
+        // word-aligned relations: 8 Philox calls give the 32 bits of this word
+        const long long rel = w / words_per_rel;
+        const long long e0 = (w - rel * words_per_rel) * 32;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const long long e = e0 + 4 * q;
+            if (e >= bits_per_rel) break;
+            const uint4 rnd = philox4x32_10(make_uint4((uint32_t)(e >> 2), (uint32_t)(r0 + rel), stream_id, step), key);
+            out |= (rnd.x >= threshold ? 1u : 0u) << (4 * q);
+            if (e + 1 < bits_per_rel) out |= (rnd.y >= threshold ? 1u : 0u) << (4 * q + 1);
+            if (e + 2 < bits_per_rel) out |= (rnd.z >= threshold ? 1u : 0u) << (4 * q + 2);
+            if (e + 3 < bits_per_rel) out |= (rnd.w >= threshold ? 1u : 0u) << (4 * q + 3);
+        }
+        words[w] = out;
+        return;
+    }
     long long cached_rel = -1, cached_ctr = -1;
     uint4 rnd = make_uint4(0, 0, 0, 0);
     for (int b = 0; b < 32; ++b) {
-        long long rel, e;
-        if (words_per_rel > 0) {
-            rel = w / words_per_rel;
-            e = (w % words_per_rel) * 32 + b;
-            if (e >= bits_per_rel) break;
-        } else {
-            const long long bit = w * 32 + b;
-            if (bit >= total_bits) break;
-            rel = bit / bits_per_rel;
-            e = bit % bits_per_rel;
-        }
+        const long long bit = w * 32 + b;
+        if (bit >= total_bits) break;
+        const long long rel = bit / bits_per_rel, e = bit % bits_per_rel;
         const long long ctr = e >> 2;
         if (rel != cached_rel || ctr != cached_ctr) {
-            rnd = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(r0 + rel), stream_id, step),
-                                make_uint2(seed_lo, seed_hi));
+            rnd = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(r0 + rel), stream_id, step), key);
             cached_rel = rel;
             cached_ctr = ctr;
         }

@@ -29,32 +29,42 @@ __device__ __forceinline__ bool mask_bit(const uint32_t *__restrict__ mask, int 
 }
 
 // ------------------------------------------------------------------------------ gather path
+// One quarter-warp (8 lanes x float4 = a 32-feature panel row) per segment, 4 segments per warp
+// in lockstep; the 8 lanes fetch 8 (column, value) pairs at a time and broadcast them inside the
+// quarter-warp; operand rows are 128-bit loads through L1.
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
 template <int P>
 __global__ void __launch_bounds__(256) spmm_seg_kernel(const SpmmArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int seg = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
-    if (seg >= a.n_seg) return;
+    const int l8 = threadIdx.x & 7;
+    const int seg = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 3);
+    const bool live = seg < a.n_seg;
 
-    int row, begin, end;
+    int row = 0, begin = 0, end = 0;
     bool single = true;
-    if (a.seg_row != nullptr) {
-        row = __ldg(a.seg_row + seg);
-        begin = __ldg(a.seg_begin + seg);
-        end = min(begin + a.seg_len, __ldg(a.rowptr + row + 1));
-        single = (__ldg(a.row_seg_ptr + row + 1) - __ldg(a.row_seg_ptr + row)) == 1;
-    } else {
-        row = seg;
-        begin = __ldg(a.rowptr + row);
-        end = __ldg(a.rowptr + row + 1);
+    if (live) {
+        if (a.seg_row != nullptr) {
+            row = __ldg(a.seg_row + seg);
+            begin = __ldg(a.seg_begin + seg);
+            end = min(begin + a.seg_len, __ldg(a.rowptr + row + 1));
+            single = (__ldg(a.row_seg_ptr + row + 1) - __ldg(a.row_seg_ptr + row)) == 1;
+        } else {
+            row = seg;
+            begin = __ldg(a.rowptr + row);
+            end = __ldg(a.rowptr + row + 1);
+        }
     }
+    const int n = end - begin;
+    int nmax = max(n, __shfl_xor_sync(kFull, n, 8));
+    nmax = max(nmax, __shfl_xor_sync(kFull, nmax, 16));
 
-    float acc[P];
+    float4 acc[P];
 #pragma unroll
-    for (int p = 0; p < P; ++p) acc[p] = 0.f;
+    for (int p = 0; p < P; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    const float *__restrict__ op = a.op + lane;
-    for (int base = begin; base < end; base += 32) {
-        const int idx = base + lane;
+    const float *__restrict__ op = a.op + (l8 << 2);
+    for (int base = 0; base < nmax; base += 8) {
+        const int idx = begin + base + l8;
         int c = 0;
         float v = 0.f;
         if (idx < end) {
@@ -62,36 +72,34 @@ __global__ void __launch_bounds__(256) spmm_seg_kernel(const SpmmArgs a) {
             v = __ldg(a.val + idx);
             if (a.col_mask) v = mask_bit(a.mask, c) ? v * a.scale : 0.f;
         }
-        const int n = min(32, end - base);
-        // padded to a multiple of 4: the padding lanes hold (col 0, value 0)
-        for (int t = 0; t < n; t += 4) {
-            int cc[4];
-            float vv[4];
+        const int cnt = min(8, nmax - base);
+#pragma unroll 4
+        for (int j = 0; j < cnt; ++j) {
+            const int cc = __shfl_sync(kFull, c, j, 8);
+            const float vv = __shfl_sync(kFull, v, j, 8);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                cc[q] = __shfl_sync(kFull, c, (t + q) & 31);
-                vv[q] = __shfl_sync(kFull, v, (t + q) & 31);
+            for (int p = 0; p < P; ++p) {
+                const float4 x = ldg4(op + ((size_t)p * a.op_rows + cc) * 32);
+                acc[p].x = fmaf(vv, x.x, acc[p].x);
+                acc[p].y = fmaf(vv, x.y, acc[p].y);
+                acc[p].z = fmaf(vv, x.z, acc[p].z);
+                acc[p].w = fmaf(vv, x.w, acc[p].w);
             }
-            float x[4][P];
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int p = 0; p < P; ++p) x[q][p] = __ldg(op + ((size_t)p * a.op_rows + cc[q]) * 32);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int p = 0; p < P; ++p) acc[p] = fmaf(vv[q], x[q][p], acc[p]);
         }
     }
+    if (!live) return;
 
     if (a.force_partial || !single) {
 #pragma unroll
-        for (int p = 0; p < P; ++p) a.partial[((size_t)seg * P + p) * 32 + lane] = acc[p];
+        for (int p = 0; p < P; ++p)
+            *reinterpret_cast<float4 *>(a.partial + ((size_t)seg * P + p) * 32 + (l8 << 2)) = acc[p];
     } else {
         float s = 1.f;
         if (a.row_mask) s = mask_bit(a.mask, row) ? a.scale : 0.f;
 #pragma unroll
-        for (int p = 0; p < P; ++p) a.out[((size_t)p * a.out_rows + row) * 32 + lane] = acc[p] * s;
+        for (int p = 0; p < P; ++p)
+            *reinterpret_cast<float4 *>(a.out + ((size_t)p * a.out_rows + row) * 32 + (l8 << 2)) =
+                make_float4(acc[p].x * s, acc[p].y * s, acc[p].z * s, acc[p].w * s);
     }
 }
 
@@ -150,17 +158,24 @@ __device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, 
                  : "memory");
 }
 
-template <int RPW>
+// Quarter-warp rows: 8 lanes x float4 = the 32 features of a panel row, so one warp works on
+// 4 adjacent output rows at once and one LDS.128 serves 4 non-zeros (4 x 128 B wavefronts).
+// Row u is owned by quarter-warp (u % 128) for the whole kernel (slot u / 128), its running sum
+// lives in registers across every relation of the CTA.
+constexpr int kQuarters = kStagedThreads / 8;  // 128 quarter-warps per CTA
+
+template <int RPQ>
 __global__ void __launch_bounds__(kStagedThreads, 1) spmm_staged_kernel(const StagedArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int tile_floats = a.n_j * 32;
-    float *tile[2] = {reinterpret_cast<float *>(smem_raw), reinterpret_cast<float *>(smem_raw) + tile_floats};
     __shared__ __align__(8) uint64_t full[2];
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int l8 = threadIdx.x & 7, qw = threadIdx.x >> 3;
     const int p = blockIdx.x % a.P, slot = blockIdx.x / a.P;
-    const int r_begin = a.slot_ptr[slot], r_end = a.slot_ptr[slot + 1];
+    const int r_begin = a.slot_ptr[slot], n_rel = a.slot_ptr[slot + 1] - r_begin;
+    const int tile_floats = a.n_j * 32;
     const uint32_t tile_bytes = (uint32_t)tile_floats * 4u;
+    const unsigned qmask = 0xffu << (lane & 24);  // the 8 lanes of this quarter-warp
 
     if (threadIdx.x == 0) {
         mbar_init(&full[0], 1);
@@ -172,15 +187,15 @@ __global__ void __launch_bounds__(kStagedThreads, 1) spmm_staged_kernel(const St
     auto issue = [&](int t) {  // thread 0 only
         const int k = a.slot_rel[r_begin + t];
         uint64_t *bar = &full[t & 1];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(bar, tile_bytes);
-        bulk_load(tile[t & 1], a.op + ((size_t)p * a.K + k) * tile_floats, tile_bytes, bar);
+        bulk_load(smem_raw + (size_t)(t & 1) * tile_bytes, a.op + ((size_t)p * a.K + k) * tile_floats, tile_bytes, bar);
     };
-    const int n_rel = r_end - r_begin;
     if (threadIdx.x == 0 && n_rel > 0) issue(0);
 
-    float acc[RPW];
+    float4 acc[RPQ];
 #pragma unroll
-    for (int s = 0; s < RPW; ++s) acc[s] = 0.f;
+    for (int s = 0; s < RPQ; ++s) acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     for (int t = 0; t < n_rel; ++t) {
         // buffer (t+1)&1 was last read for relation t-1; every warp passed the barrier that
@@ -188,53 +203,89 @@ __global__ void __launch_bounds__(kStagedThreads, 1) spmm_staged_kernel(const St
         if (threadIdx.x == 0 && t + 1 < n_rel) issue(t + 1);
         const int k = a.slot_rel[r_begin + t];
         const int *__restrict__ rp = a.rowptr + (size_t)k * (a.n_i + 1);
-        // lane s of this warp fetches the row pointers of the warp's s-th row
+        // lane s of the quarter-warp fetches the row pointers of its s-th row
         int my_b = 0, my_e = 0;
         {
-            const int u = warp + lane * kStagedWarps;
-            if (lane < RPW && u < a.n_i) {
+            const int u = qw + l8 * kQuarters;
+            if (l8 < RPQ && u < a.n_i) {
                 my_b = __ldg(rp + u);
                 my_e = __ldg(rp + u + 1);
             }
         }
+        // first 8 entries of a row slot are fetched one slot ahead of their use
+        auto first_chunk = [&](int s, int &off, float &v) {
+            const int b = __shfl_sync(qmask, my_b, s, 8), e = __shfl_sync(qmask, my_e, s, 8);
+            const int idx = b + l8;
+            off = 0;
+            v = 0.f;
+            if (idx < e) {
+                off = __ldg(a.col + idx) << 7;  // byte offset of the operand row in the tile
+                v = __ldg(a.val + idx);
+            }
+        };
+        int next_off;
+        float next_v;
+        first_chunk(0, next_off, next_v);
         mbar_wait(&full[t & 1], (uint32_t)((t >> 1) & 1));
-        const float *__restrict__ x = tile[t & 1] + lane;
-        const int mask_base = k * a.n_j;
+        unsigned char *tile = smem_raw + (size_t)(t & 1) * tile_bytes;
+        if (a.mask != nullptr) {
+            // layer-1 dropout on identity features drops whole operand rows: zero them in the
+            // staged tile (the 1/keep scale is applied once, to the final sums)
+            const int base_bit = k * a.n_j;
+            for (int c = threadIdx.x >> 3; c < a.n_j; c += kQuarters)
+                if (!mask_bit(a.mask, base_bit + c))
+                    *reinterpret_cast<float4 *>(tile + ((size_t)c << 7) + (l8 << 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+        }
+        const unsigned char *xrow = tile + (l8 << 4);
 #pragma unroll
-        for (int s = 0; s < RPW; ++s) {
-            const int begin = __shfl_sync(kFull, my_b, s), end = __shfl_sync(kFull, my_e, s);
-            float sum = 0.f;
-            for (int base = begin; base < end; base += 32) {
-                const int idx = base + lane;
-                int c = 0;
-                float v = 0.f;
-                if (idx < end) {
-                    c = __ldg(a.col + idx);
-                    v = __ldg(a.val + idx);
-                    if (a.mask != nullptr) v = mask_bit(a.mask, mask_base + c) ? v * a.scale : 0.f;
+        for (int s = 0; s < RPQ; ++s) {
+            const int b = __shfl_sync(qmask, my_b, s, 8), e = __shfl_sync(qmask, my_e, s, 8);
+            int n = e - b;  // non-zeros of this quarter-warp's row; the warp runs to the longest of its 4 rows
+            int nmax = max(n, __shfl_xor_sync(kFull, n, 8));
+            nmax = max(nmax, __shfl_xor_sync(kFull, nmax, 16));
+            int off = next_off;
+            float v = next_v;
+            if (s + 1 < RPQ) first_chunk(s + 1, next_off, next_v);
+            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int base = 0; base < nmax; base += 8) {
+                if (base > 0) {
+                    const int idx = b + base + l8;
+                    off = 0;
+                    v = 0.f;
+                    if (idx < e) {
+                        off = __ldg(a.col + idx) << 7;
+                        v = __ldg(a.val + idx);
+                    }
                 }
-                const int n = min(32, end - base);
-                for (int q = 0; q < n; q += 4) {
-                    const int c0 = __shfl_sync(kFull, c, q), c1 = __shfl_sync(kFull, c, (q + 1) & 31);
-                    const int c2 = __shfl_sync(kFull, c, (q + 2) & 31), c3 = __shfl_sync(kFull, c, (q + 3) & 31);
-                    const float v0 = __shfl_sync(kFull, v, q), v1 = __shfl_sync(kFull, v, (q + 1) & 31);
-                    const float v2 = __shfl_sync(kFull, v, (q + 2) & 31), v3 = __shfl_sync(kFull, v, (q + 3) & 31);
-                    const float x0 = x[c0 * 32], x1 = x[c1 * 32], x2 = x[c2 * 32], x3 = x[c3 * 32];
-                    sum = fmaf(v0, x0, sum);
-                    sum = fmaf(v1, x1, sum);
-                    sum = fmaf(v2, x2, sum);
-                    sum = fmaf(v3, x3, sum);
+                const int cnt = min(8, nmax - base);
+#pragma unroll 4
+                for (int j = 0; j < cnt; ++j) {
+                    const int o = __shfl_sync(kFull, off, j, 8);
+                    const float vv = __shfl_sync(kFull, v, j, 8);
+                    const float4 x = *reinterpret_cast<const float4 *>(xrow + o);
+                    sum.x = fmaf(vv, x.x, sum.x);
+                    sum.y = fmaf(vv, x.y, sum.y);
+                    sum.z = fmaf(vv, x.z, sum.z);
+                    sum.w = fmaf(vv, x.w, sum.w);
                 }
             }
-            acc[s] += sum;
+            acc[s].x += sum.x;
+            acc[s].y += sum.y;
+            acc[s].z += sum.z;
+            acc[s].w += sum.w;
         }
         __syncthreads();
     }
 
+    const float sc = a.mask != nullptr ? a.scale : 1.f;
 #pragma unroll
-    for (int s = 0; s < RPW; ++s) {
-        const int u = warp + s * kStagedWarps;
-        if (u < a.n_i) a.partial[(((size_t)slot * a.P + p) * a.n_i + u) * 32 + lane] = acc[s];
+    for (int s = 0; s < RPQ; ++s) {
+        const int u = qw + s * kQuarters;
+        if (u < a.n_i)
+            *reinterpret_cast<float4 *>(a.partial + (((size_t)slot * a.P + p) * a.n_i + u) * 32 + (l8 << 2)) =
+                make_float4(acc[s].x * sc, acc[s].y * sc, acc[s].z * sc, acc[s].w * sc);
     }
 }
 
@@ -243,8 +294,8 @@ __global__ void __launch_bounds__(kStagedThreads, 1) spmm_staged_kernel(const St
 // ------------------------------------------------------------------------------ launchers
 void launch_spmm(const SpmmArgs &a, int P, cudaStream_t s) {
     if (a.n_seg == 0) return;
-    const int warps_per_block = 8;
-    dim3 grid((unsigned)((a.n_seg + warps_per_block - 1) / warps_per_block)), block(warps_per_block * 32);
+    const int segs_per_block = 32;  // 256 threads = 32 quarter-warps
+    dim3 grid((unsigned)((a.n_seg + segs_per_block - 1) / segs_per_block)), block(256);
     switch (P) {
         case 1: spmm_seg_kernel<1><<<grid, block, 0, s>>>(a); break;
         case 2: spmm_seg_kernel<2><<<grid, block, 0, s>>>(a); break;
@@ -270,28 +321,29 @@ void launch_seg_reduce(const SpmmArgs &a, const int *multi_rows, int n_multi, in
 size_t staged_smem_bytes(int n_j) { return (size_t)2 * n_j * 32 * sizeof(float); }
 
 bool staged_supported(int n_i, int n_j, int K) {
-    return K >= 8 && staged_smem_bytes(n_j) <= 200 * 1024 && n_i <= 32 * kStagedWarps;
+    return K >= 8 && staged_smem_bytes(n_j) <= 200 * 1024 && n_i <= 8 * kQuarters;
 }
 
-template <int RPW>
+template <int RPQ>
 static void launch_staged_t(const StagedArgs &a, cudaStream_t s) {
     const size_t smem = staged_smem_bytes(a.n_j);
     static bool configured = false;
     if (!configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(spmm_staged_kernel<RPW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_CHECK(cudaFuncSetAttribute(spmm_staged_kernel<RPQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         200 * 1024));
         configured = true;
     }
-    spmm_staged_kernel<RPW><<<a.n_slots * a.P, kStagedThreads, smem, s>>>(a);
+    spmm_staged_kernel<RPQ><<<a.n_slots * a.P, kStagedThreads, smem, s>>>(a);
     CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_spmm_staged(const StagedArgs &a, int rows_per_warp, cudaStream_t s) {
-    if (rows_per_warp <= 8) launch_staged_t<8>(a, s);
-    else if (rows_per_warp <= 16) launch_staged_t<16>(a, s);
-    else if (rows_per_warp <= 24) launch_staged_t<24>(a, s);
-    else if (rows_per_warp <= 32) launch_staged_t<32>(a, s);
-    else DGN_FAIL(DGN_ERR_UNSUPPORTED, "staged spmm: %d rows per warp", rows_per_warp);
+void launch_spmm_staged(const StagedArgs &a, cudaStream_t s) {
+    const int rpq = (a.n_i + kQuarters - 1) / kQuarters;  // rows per quarter-warp
+    if (rpq <= 2) launch_staged_t<2>(a, s);
+    else if (rpq <= 4) launch_staged_t<4>(a, s);
+    else if (rpq <= 6) launch_staged_t<6>(a, s);
+    else if (rpq <= 8) launch_staged_t<8>(a, s);
+    else DGN_FAIL(DGN_ERR_UNSUPPORTED, "staged spmm: %d rows per quarter-warp", rpq);
 }
 
 }  // namespace dgn
