@@ -158,7 +158,7 @@ struct Group {
     float *P2 = nullptr, *dS = nullptr, *G2 = nullptr, *bwd_partial = nullptr, *dW2part = nullptr, *dHpart = nullptr;
     uint32_t *mask1 = nullptr, *mask2 = nullptr;
     long long mask1_words = 0, mask2_words = 0;
-    int rows_per_chunk = 0, n_row_chunks = 1, rel_per_chunk = 0, n_kchunks = 1;
+    int n_rb = 1, slots_proj = 1, slots_dh = 1;  // dense layer-2 kernels: row blocks, persistent CTAs per block
     std::vector<uint32_t *> thr;  // per relation
     std::vector<int> thr_n;
 };
@@ -319,19 +319,13 @@ void build_group(dgn_graph *g, Group &G) {
     G.mask1 = dev_alloc<uint32_t>((size_t)G.mask1_words);
     G.mask2 = dev_alloc<uint32_t>((size_t)G.mask2_words);
 
-    // dW2: split the n_j rows of one relation into chunks when there are few relations
-    G.n_row_chunks = 1;
-    if ((long long)K < 2LL * g->n_sm) G.n_row_chunks = (int)std::min<long long>((n_j + 511) / 512, (2LL * g->n_sm + K - 1) / K);
-    G.n_row_chunks = std::max(1, G.n_row_chunks);
-    G.rows_per_chunk = ((n_j + G.n_row_chunks - 1) / G.n_row_chunks + 31) / 32 * 32;
-    G.n_row_chunks = (n_j + G.rows_per_chunk - 1) / G.rows_per_chunk;
-    if (G.n_row_chunks > 1) G.dW2part = dev_alloc<float>((size_t)K * G.n_row_chunks * g->d1 * g->d2);
-    // dH: relations are summed inside a chunk, chunks are summed by relu_bwd
-    const int row_tiles = (n_j + 127) / 128;
-    G.n_kchunks = std::max(1, std::min(K, (4 * g->n_sm + row_tiles - 1) / row_tiles));
-    G.rel_per_chunk = (K + G.n_kchunks - 1) / G.n_kchunks;
-    G.n_kchunks = (K + G.rel_per_chunk - 1) / G.rel_per_chunk;
-    G.dHpart = dev_alloc<float>((size_t)G.n_kchunks * panel_floats(P1, n_j));
+    // dense layer-2 kernels: persistent CTAs, one per (row block, slot of relations)
+    const int RB = dense_row_block(g->d1);
+    G.n_rb = (n_j + RB - 1) / RB;
+    G.slots_proj = std::max(1, std::min(K, g->n_sm / G.n_rb));
+    G.slots_dh = std::max(1, std::min(K, g->n_sm / (P1 * G.n_rb)));
+    if (G.n_rb > 1) G.dW2part = dev_alloc<float>((size_t)K * G.n_rb * g->d1 * g->d2);
+    G.dHpart = dev_alloc<float>((size_t)G.slots_dh * panel_floats(P1, n_j));
 }
 
 uint32_t dropout_threshold(float rate) {
@@ -410,6 +404,7 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step) {
         DenseArgs a = {};
         a.H = g->types[G.j].H, a.W2 = g->params + G.w2_off, a.P2 = G.P2;
         a.mask = drop ? G.mask2 : nullptr, a.scale = scale, a.K = G.K, a.n_j = G.n_j;
+        a.n_rb = G.n_rb, a.n_slots = G.slots_proj;
         launch_project(a, g->d1, g->d2, s);
         g->launches++;
     }
@@ -460,20 +455,21 @@ void run_backward(dgn_graph *g, float rate) {
         DenseArgs a = {};
         a.H = g->types[G.j].H, a.W2 = g->params + G.w2_off, a.G2 = G.G2;
         a.mask = drop ? G.mask2 : nullptr, a.scale = scale, a.K = G.K, a.n_j = G.n_j;
-        a.rows_per_chunk = G.rows_per_chunk, a.n_row_chunks = G.n_row_chunks;
-        a.rel_per_chunk = G.rel_per_chunk, a.n_kchunks = G.n_kchunks;
-        a.dW2 = G.n_row_chunks > 1 ? G.dW2part : g->grads + G.w2_off;
+        a.n_rb = G.n_rb;
+        a.dW2 = G.n_rb > 1 ? G.dW2part : g->grads + G.w2_off;
         a.dHpart = G.dHpart;
         {
             PhaseScope ph(g, "dw2", gi);
+            a.n_slots = G.slots_proj;
             launch_dw2(a, g->d1, g->d2, s);
             g->launches++;
-            if (G.n_row_chunks > 1) {
-                launch_dw2_reduce(G.dW2part, g->grads + G.w2_off, G.K, G.n_row_chunks, g->d1 * g->d2, s);
+            if (G.n_rb > 1) {
+                launch_dw2_reduce(G.dW2part, g->grads + G.w2_off, G.K, G.n_rb, g->d1 * g->d2, s);
                 g->launches++;
             }
         }
         PhaseScope ph(g, "dh", gi);
+        a.n_slots = G.slots_dh;
         launch_dh(a, g->d1, g->d2, s);
         g->launches++;
     }
@@ -486,7 +482,7 @@ void run_backward(dgn_graph *g, float rate) {
             r.H = T.H, r.dA = T.dA;
             for (int gi : T.col_groups) {
                 r.g[r.n_groups].part = g->groups[gi].dHpart;
-                r.g[r.n_groups].n_chunks = g->groups[gi].n_kchunks;
+                r.g[r.n_groups].n_chunks = g->groups[gi].slots_dh;
                 r.n_groups++;
             }
             launch_relu_bwd(r, P1, s);

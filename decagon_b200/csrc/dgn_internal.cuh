@@ -143,13 +143,13 @@ struct DenseArgs {
     const float *H, *W2;
     float *P2;        // forward output
     const float *G2;  // backward input
-    float *dW2;       // [K][D1*D2] (direct) or partial [K][n_chunks][D1*D2]
-    float *dHpart;    // [n_kchunks][P1][n_j][32]
+    float *dW2;       // [K][n_rb][D1*D2]: one partial per row block (n_rb == 1: the gradient itself)
+    float *dHpart;    // [n_slots][P1][n_j][32]: one partial per slot of relations
     const uint32_t *mask;  // [K*n_j*P1] words or null
     float scale;
     int K, n_j;
-    int rows_per_chunk, n_row_chunks;  // dW2 split over rows
-    int rel_per_chunk, n_kchunks;      // dH split over relations
+    int n_rb;     // row blocks of dense_row_block(D1) rows
+    int n_slots;  // persistent CTAs per row block; slot s owns relations [s K / n_slots, (s+1) K / n_slots)
 };
 
 struct DecodeArgs {
@@ -190,6 +190,7 @@ void launch_l2norm_bwd(const L2BwdArgs &a, int P, cudaStream_t s);
 void launch_relu_bwd(const ReluBwdArgs &a, int P, cudaStream_t s);
 void launch_gen_mask(uint32_t *words, long long n_words, long long bits_per_rel, int words_per_rel_or_0, int r0,
                      uint32_t stream_id, uint32_t step, uint64_t seed, uint32_t threshold, cudaStream_t s);
+int dense_row_block(int D1);
 void launch_project(const DenseArgs &a, int D1, int D2, cudaStream_t s);
 void launch_dw2(const DenseArgs &a, int D1, int D2, cudaStream_t s);
 void launch_dw2_reduce(const float *part, float *out, int K, int n_chunks, int elems, cudaStream_t s);
