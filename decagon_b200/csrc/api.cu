@@ -104,12 +104,12 @@ struct SlotTable {
 
 // longest-processing-time assignment of relations to persistent CTAs, balanced by nnz;
 // inside a slot relations stay in ascending order (fixed summation order)
-SlotTable build_slots(const std::vector<HostCsr> &rels, int n_slots) {
-    const int K = (int)rels.size();
+SlotTable build_slots(const std::vector<long long> &weight, int n_slots) {
+    const int K = (int)weight.size();
     n_slots = std::max(1, std::min(n_slots, K));
     std::vector<int> order(K);
     std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return rels[x].nnz() > rels[y].nnz(); });
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return weight[x] > weight[y]; });
     typedef std::pair<long long, int> Load;
     std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
     for (int s = 0; s < n_slots; ++s) heap.push(Load(0, s));
@@ -118,7 +118,7 @@ SlotTable build_slots(const std::vector<HostCsr> &rels, int n_slots) {
         Load l = heap.top();
         heap.pop();
         lists[l.second].push_back(k);
-        heap.push(Load(l.first + rels[k].nnz() + rels[k].n_cols, l.second));
+        heap.push(Load(l.first + weight[k], l.second));
     }
     std::vector<int> ptr(1, 0), rel;
     for (auto &l : lists) {
@@ -131,6 +131,105 @@ SlotTable build_slots(const std::vector<HostCsr> &rels, int n_slots) {
     t.ptr = dev_upload(ptr);
     t.rel = dev_upload(rel);
     return t;
+}
+
+// Warp-task streams of the staged v3 kernels (TaskArgs in dgn_internal.cuh)
+struct TaskCsr {
+    int n_warps = 0, rpq = 0, orow_stride = 0;
+    int *hdr = nullptr, *orow = nullptr;
+    int4 *ent = nullptr;
+    std::vector<long long> rel_steps;  // pair-steps of the longest warp stream per relation (load balance weight)
+};
+void free_task(TaskCsr &c) {
+    dev_free(c.hdr);
+    dev_free(c.orow);
+    dev_free(c.ent);
+    c = TaskCsr();
+}
+
+// rels: K matrices with n_rows rows each.  Rows are sorted by length (summed over the relations, or
+// per relation when per_rel); consecutive groups of 4 go to the n_warps warps in snake order; slot s of
+// warp w is its s-th group.  round_rpq: slots per warp rounded up to an even count (the forward kernel
+// is compiled for 2, 4, 6, 8).
+TaskCsr build_task_csr(const std::vector<HostCsr> &rels, int n_rows, int n_warps, bool per_rel, bool round_rpq) {
+    const int K = (int)rels.size();
+    const int n_groups = (n_rows + 3) / 4;
+    int rpq = std::max(1, (n_groups + n_warps - 1) / n_warps);
+    if (round_rpq) rpq = (rpq + 1) / 2 * 2;
+    DGN_REQUIRE(rpq <= 8, "staged spmm: %d rows per quarter-warp (at most 8)", rpq);
+    const int n_slots = n_warps * rpq;  // (warp, slot) pairs
+    TaskCsr out;
+    out.n_warps = n_warps, out.rpq = rpq, out.orow_stride = per_rel ? n_slots * 4 : 0;
+    out.rel_steps.assign(K, 0);
+    std::vector<int> hdr((size_t)K * n_warps * 8, 0), orow((size_t)(per_rel ? K : 1) * n_slots * 4, -1);
+    std::vector<int4> ent;
+    long long nnz = 0;
+    for (auto &c : rels) nnz += c.nnz();
+    ent.reserve((size_t)(nnz * 3 / 4 + 1024));
+    std::vector<long long> weight((size_t)n_rows, 0);
+    std::vector<int> order((size_t)n_rows), map((size_t)n_slots * 4);
+    auto make_map = [&]() {  // map[(w * rpq + s) * 4 + quarter] = row
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return weight[x] > weight[y]; });
+        std::fill(map.begin(), map.end(), -1);
+        for (int j = 0; j < n_groups; ++j) {
+            const int s = j / n_warps, jj = j % n_warps;
+            const int w = (s & 1) ? n_warps - 1 - jj : jj;
+            for (int i = 0; i < 4 && 4 * j + i < n_rows; ++i) map[(size_t)(w * rpq + s) * 4 + i] = order[(size_t)4 * j + i];
+        }
+    };
+    if (!per_rel) {
+        for (auto &c : rels)
+            for (int u = 0; u < n_rows; ++u) weight[u] += c.rowptr[u + 1] - c.rowptr[u];
+        make_map();
+        std::copy(map.begin(), map.end(), orow.begin());
+    }
+    const int4 pad = make_int4(0, 0, 0, 0);
+    for (int k = 0; k < K; ++k) {
+        const HostCsr &c = rels[k];
+        if (per_rel) {
+            for (int u = 0; u < n_rows; ++u) weight[u] = c.rowptr[u + 1] - c.rowptr[u];
+            make_map();
+            std::copy(map.begin(), map.end(), orow.begin() + (size_t)k * n_slots * 4);
+        }
+        for (int w = 0; w < n_warps; ++w) {
+            int *h = hdr.data() + ((size_t)k * n_warps + w) * 8;
+            DGN_REQUIRE(ent.size() / 4 < (size_t)INT32_MAX, "staged spmm: stream offsets overflow int32");
+            h[0] = (int)(ent.size() / 4);
+            long long steps = 0;
+            for (int s = 0; s < rpq; ++s) {
+                int cnt = 0;
+                for (int q = 0; q < 4; ++q) {
+                    const int u = map[(size_t)(w * rpq + s) * 4 + q];
+                    if (u >= 0) cnt = std::max(cnt, c.rowptr[u + 1] - c.rowptr[u]);
+                }
+                const int n2 = (cnt + 1) / 2;
+                DGN_REQUIRE(n2 <= 0xffff, "staged spmm: row with %d non-zeros", cnt);
+                h[1 + (s >> 1)] |= n2 << ((s & 1) * 16);
+                steps += n2;
+                const size_t base = ent.size();
+                ent.resize(base + (size_t)n2 * 4, pad);
+                for (int q = 0; q < 4; ++q) {
+                    const int u = map[(size_t)(w * rpq + s) * 4 + q];
+                    if (u < 0) continue;
+                    const int b = c.rowptr[u], n = c.rowptr[u + 1] - b;
+                    for (int i = 0; i < n; ++i) {
+                        int4 &x = ent[base + (size_t)(i >> 1) * 4 + q];
+                        int bits;
+                        memcpy(&bits, &c.val[b + i], sizeof(float));
+                        if (i & 1) x.z = c.col[b + i] << 7, x.w = bits;
+                        else x.x = c.col[b + i] << 7, x.y = bits;
+                    }
+                }
+            }
+            out.rel_steps[k] = std::max(out.rel_steps[k], steps);
+        }
+    }
+    ent.resize(ent.size() + 16, pad);  // the kernels fetch two pair-steps ahead
+    out.hdr = dev_upload(hdr);
+    out.orow = dev_upload(orow);
+    out.ent = dev_upload(ent);
+    return out;
 }
 
 struct NodeType {
@@ -151,6 +250,10 @@ struct Group {
     SegTable fwd_seg, bwd_seg;
     bool staged = false;
     SlotTable slots1, slots2;
+    int staged_version = 3;      // 2: spmm_staged_kernel, 3: spmm_staged3_kernel (position order, mbarrier pipeline)
+    bool tstaged = false;        // backward products through spmm_tstaged_kernel
+    TaskCsr task_fwd, task_bwd;
+    SlotTable slots_bwd;
     // parameter arena offsets (floats)
     size_t w1_off = 0, w2_off = 0, glb_off = 0, loc_off = 0, loc_per_rel = 0;
     // work buffers
@@ -177,7 +280,8 @@ struct dgn_graph {
     std::vector<Group> groups;
     std::vector<std::pair<int, int>> flat;  // r -> (group, k)
     bool finalized = false;
-    bool allow_staged = true;
+    bool allow_staged = true, allow_tstaged = true;
+    int staged_version = 3;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     // parameters
@@ -236,6 +340,10 @@ void free_group_device(Group &G) {
     dev_free(G.slots1.rel);
     dev_free(G.slots2.ptr);
     dev_free(G.slots2.rel);
+    dev_free(G.slots_bwd.ptr);
+    dev_free(G.slots_bwd.rel);
+    free_task(G.task_fwd);
+    free_task(G.task_bwd);
     float **bufs[] = {&G.part1, &G.part2, &G.Y1, &G.n1, &G.Y2, &G.n2, &G.P2, &G.dS, &G.G2, &G.bwd_partial, &G.dW2part, &G.dHpart};
     for (float **b : bufs) dev_free(*b);
     dev_free(G.mask1);
@@ -298,9 +406,25 @@ void build_group(dgn_graph *g, Group &G) {
     G.bwd_seg = build_segments(bwd, std::min(256, std::max(32, seg_len)), true);
     if (!G.bwd_seg.trivial) G.bwd_partial = dev_alloc<float>(panel_floats(P1, G.bwd_seg.n_seg));
 
+    G.staged_version = g->staged_version;
+    if (G.staged && G.staged_version == 3 && !staged3_supported(n_i, n_j, K)) G.staged_version = 2;
+    G.tstaged = G.staged && g->allow_tstaged && tstaged_supported(n_i, n_j, K, P1);
+    std::vector<long long> w_fwd(K), w_bwd(K);
+    for (int k = 0; k < K; ++k) w_fwd[k] = w_bwd[k] = G.rel[k].nnz() + G.rel[k].n_cols;
+    if (G.staged && G.staged_version == 3) {
+        G.task_fwd = build_task_csr(G.rel, n_i, kS3Warps, false, true);
+        for (int k = 0; k < K; ++k) w_fwd[k] = G.task_fwd.rel_steps[k] + 64;
+    }
+    if (G.tstaged) {
+        std::vector<HostCsr> relt(K);
+        for (int k = 0; k < K; ++k) csr_transpose(G.rel[k], relt[k]);
+        G.task_bwd = build_task_csr(relt, n_j, kTsWarps, true, false);
+        for (int k = 0; k < K; ++k) w_bwd[k] = G.task_bwd.rel_steps[k] + 16;
+        G.slots_bwd = build_slots(w_bwd, g->n_sm);
+    }
     if (G.staged) {
-        G.slots1 = build_slots(G.rel, std::max(1, g->n_sm / P1));
-        G.slots2 = build_slots(G.rel, g->n_sm);
+        G.slots1 = build_slots(w_fwd, std::max(1, g->n_sm / P1));
+        G.slots2 = build_slots(w_fwd, g->n_sm);
         G.part1 = dev_alloc<float>((size_t)G.slots1.n_slots * panel_floats(P1, n_i));
         G.part2 = dev_alloc<float>((size_t)G.slots2.n_slots * panel_floats(1, n_i));
     } else {
@@ -350,7 +474,16 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step) {
     }
     auto spmm_fwd = [&](Group &G, const float *op, int P, long long op_rows, float *part, const SlotTable &slots,
                         const uint32_t *mask) {
-        if (G.staged) {
+        if (G.staged && G.staged_version == 3) {
+            TaskArgs a = {};
+            a.hdr = G.task_fwd.hdr, a.ent = G.task_fwd.ent, a.orow = G.task_fwd.orow, a.orow_stride = 0;
+            a.K = G.K, a.n_warps = G.task_fwd.n_warps, a.rpq = G.task_fwd.rpq;
+            a.n_out_rows = G.n_i, a.n_op_rows = G.n_j;
+            a.op = op, a.P = P;
+            a.slot_ptr = slots.ptr, a.slot_rel = slots.rel, a.n_slots = slots.n_slots;
+            a.out = part, a.mask = mask, a.scale = scale;
+            launch_spmm_staged3(a, s);
+        } else if (G.staged) {
             StagedArgs a = {};
             a.rowptr = G.relcsr.rowptr, a.col = G.relcsr.col, a.val = G.relcsr.val;
             a.K = G.K, a.n_i = G.n_i, a.n_j = G.n_j;
@@ -425,6 +558,18 @@ void run_backward(dgn_graph *g, float rate) {
     const bool drop = rate > 0.f;
     const float scale = drop ? 1.f / (1.f - rate) : 1.f;
     auto spmm_bwd = [&](Group &G, int P, float *out, long long out_rows, const uint32_t *row_mask) {
+        if (G.tstaged) {
+            TaskArgs a = {};
+            a.hdr = G.task_bwd.hdr, a.ent = G.task_bwd.ent, a.orow = G.task_bwd.orow, a.orow_stride = G.task_bwd.orow_stride;
+            a.K = G.K, a.n_warps = G.task_bwd.n_warps, a.rpq = G.task_bwd.rpq;
+            a.n_out_rows = G.n_j, a.n_op_rows = G.n_i;
+            a.op = G.dS, a.P = P;
+            a.slot_ptr = G.slots_bwd.ptr, a.slot_rel = G.slots_bwd.rel, a.n_slots = G.slots_bwd.n_slots;
+            a.out = out, a.mask = row_mask, a.scale = scale;
+            launch_spmm_tstaged(a, s);
+            g->launches++;
+            return;
+        }
         SpmmArgs a = {};
         a.rowptr = G.bwd.rowptr, a.col = G.bwd.col, a.val = G.bwd.val;
         a.seg_row = G.bwd_seg.seg_row, a.seg_begin = G.bwd_seg.seg_begin, a.row_seg_ptr = G.bwd_seg.row_seg_ptr;
@@ -730,6 +875,10 @@ extern "C" int dgn_graph_create(dgn_graph **out, int device, int n_types, const 
     }
     const char *env = getenv("DGN_DISABLE_STAGED");
     g->allow_staged = !(env && env[0] == '1');
+    env = getenv("DGN_STAGED_VERSION");
+    if (env && env[0] == '2') g->staged_version = 2;
+    env = getenv("DGN_DISABLE_TSTAGED");
+    g->allow_tstaged = !(env && env[0] == '1');
     *out = g.release();
     DGN_API_END
 }

@@ -108,6 +108,30 @@ struct StagedArgs {
     float scale;
 };
 
+// Staged SpMM v3 ("warp-task streams").  The 4 quarter-warps of a warp work on 4 rows in lockstep;
+// rows are sorted by non-zero count (summed over the relations, or per relation) and consecutive
+// groups of 4 are dealt to the warps in snake order, so lockstep rows have similar lengths and every
+// warp gets the same share of the work.  For every (relation k, warp w) the non-zeros are laid out as
+// ONE flat stream the warp reads front to back: slot s (the s-th row group of the warp) contributes
+// cnt(k, w, s) pair-steps, a pair-step is 4 x int4 = one {offset0, value0, offset1, value1} per
+// quarter-warp (offset = byte offset of the operand row in a [rows][32] tile; padding = (0, 0.0f)).
+struct TaskArgs {
+    const int *hdr;      // [K][n_warps][8]: [0] first pair-step of the stream, [1..4] 8 x uint16 pair-step counts
+    const int4 *ent;     // pair-steps
+    const int *orow;     // result row of (k, w, s, quarter) or -1: [n_warps * rpq * 4] if orow_stride == 0 else [K][...]
+    int orow_stride;
+    int K, n_warps, rpq;
+    int n_out_rows;      // rows of one relation's result
+    int n_op_rows;       // rows of the dense operand (tile rows forward, dS rows backward)
+    const float *op;     // forward: tile (p, k) at op + ((p * K + k) * n_op_rows) * 32;  backward: [P][n_op_rows][32]
+    int P;
+    const int *slot_ptr, *slot_rel;
+    int n_slots;
+    float *out;          // forward: partial [n_slots][P][n_out_rows][32];  backward: [P][K * n_out_rows][32]
+    const uint32_t *mask;  // forward: bit k * n_op_rows + operand row;  backward: bit k * n_out_rows + result row
+    float scale;
+};
+
 struct EpiGroup {
     const float *partial;
     const int *row_seg_ptr;  // segment mode; null => slot mode
@@ -184,6 +208,12 @@ void launch_spmm(const SpmmArgs &a, int P, cudaStream_t s);
 void launch_seg_reduce(const SpmmArgs &a, const int *multi_rows, int n_multi, int P, cudaStream_t s);
 void launch_spmm_staged(const StagedArgs &a, cudaStream_t s);
 size_t staged_smem_bytes(int n_j);
+constexpr int kS3Warps = 31;   // forward v3: 31 consumer warps + 1 TMA producer warp
+constexpr int kTsWarps = 32;   // backward: 32 consumer warps, operand resident in shared memory
+void launch_spmm_staged3(const TaskArgs &a, cudaStream_t s);
+void launch_spmm_tstaged(const TaskArgs &a, cudaStream_t s);
+bool staged3_supported(int n_i, int n_j, int K);
+bool tstaged_supported(int n_i, int n_j, int K, int P);
 bool staged_supported(int n_i, int n_j, int K);
 void launch_node_epilogue(const EpiArgs &a, int P, cudaStream_t s);
 void launch_l2norm_bwd(const L2BwdArgs &a, int P, cudaStream_t s);

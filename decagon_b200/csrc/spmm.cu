@@ -289,6 +289,204 @@ __global__ void __launch_bounds__(kStagedThreads, 1) spmm_staged_kernel(const St
     }
 }
 
+
+// ------------------------------------------------------------------------------ staged path v3
+// Warp-task streams (TaskArgs).  The inner loop is LDG.128 (two steps of the stream, fetched two
+// pair-steps ahead) + 2 x (LDS.128 + 4 FFMA): no row pointers, no shuffles, no per-row control
+// beyond one counter.  Forward: operand tiles move through a full / ready / empty mbarrier pipeline
+// run by a dedicated producer warp (TMA bulk copy, then layer-1 dropout = zeroing the dropped operand
+// rows in the tile), there is NO CTA-wide barrier per relation; the row sums of all relations of the
+// CTA stay in registers.
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ int4 ldg_int4(const int4 *p) { return __ldg(p); }
+__device__ __forceinline__ void fma4(float4 &acc, float v, const float4 &x) {
+    acc.x = fmaf(v, x.x, acc.x);
+    acc.y = fmaf(v, x.y, acc.y);
+    acc.z = fmaf(v, x.z, acc.z);
+    acc.w = fmaf(v, x.w, acc.w);
+}
+// acc[p] += value * tile_p[row] for one stream step (offset < 0: padding, nothing is read): predicated
+// LDS.128 + FFMA so that the padded quarter-warps of a step neither branch nor cost a shared-memory wavefront
+// one stream step: acc += value * tile[row].  Padding steps carry (offset 0, value 0): they read row 0 and add
+// nothing, so the loop has no predicates or branches.
+__device__ __forceinline__ void gather_fma(float4 &acc, const unsigned char *xrow, int off, int vbits) {
+    fma4(acc, __int_as_float(vbits), *reinterpret_cast<const float4 *>(xrow + off));
+}
+
+__device__ __forceinline__ int task_count(int h, int s, int lane_base) {
+    // uint16 count of slot s: word 1 + s / 2 of the header, held by lane (1 + s / 2) of every quarter-warp
+    return (__shfl_sync(kFull, h, lane_base + 1 + (s >> 1)) >> ((s & 1) * 16)) & 0xffff;
+}
+
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// n2 pair-steps of a warp stream starting at ep (this quarter-warp's int4 of the first pair-step;
+// consecutive pair-steps are 4 int4 apart).  Four pair-steps per iteration with their loads issued
+// together and the next iteration's lines prefetched into L1.
+template <typename F>
+__device__ __forceinline__ void stream_steps(const int4 *__restrict__ &ep, int n2, F &&step) {
+    int ps = 0;
+#pragma unroll 1
+    for (; ps + 4 <= n2; ps += 4) {
+        const int4 e0 = ldg_int4(ep), e1 = ldg_int4(ep + 4), e2 = ldg_int4(ep + 8), e3 = ldg_int4(ep + 12);
+        prefetch_l1(ep + 16);
+        prefetch_l1(ep + 24);
+        ep += 16;
+        step(e0.x, e0.y), step(e0.z, e0.w);
+        step(e1.x, e1.y), step(e1.z, e1.w);
+        step(e2.x, e2.y), step(e2.z, e2.w);
+        step(e3.x, e3.y), step(e3.z, e3.w);
+    }
+#pragma unroll 1
+    for (; ps < n2; ++ps) {
+        const int4 e0 = ldg_int4(ep);
+        ep += 4;
+        step(e0.x, e0.y), step(e0.z, e0.w);
+    }
+}
+
+// slots S .. RPQ - 1 of one warp stream (compile-time recursion keeps acc[] in registers)
+template <int S, int RPQ>
+__device__ __forceinline__ void stream_slots(float4 (&acc)[RPQ], int h, const int4 *__restrict__ &ep, const unsigned char *xrow) {
+    if constexpr (S < RPQ) {
+        stream_steps(ep, task_count(h, S, 0), [&](int off, int vbits) { gather_fma(acc[S], xrow, off, vbits); });
+        stream_slots<S + 1, RPQ>(acc, h, ep, xrow);
+    }
+}
+
+template <int RPQ>
+__global__ void __launch_bounds__(kStagedThreads, 1) spmm_staged3_kernel(const TaskArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full[2], ready[2], empty[2];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int l8 = lane & 7, quarter = lane >> 3;
+    const int p = blockIdx.x % a.P, slot = blockIdx.x / a.P;
+    const int r_begin = a.slot_ptr[slot], n_rel = a.slot_ptr[slot + 1] - r_begin;
+    const uint32_t tile_bytes = (uint32_t)a.n_op_rows * 128u;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&full[b], 1);
+            mbar_init(&ready[b], 1);
+            mbar_init(&empty[b], kS3Warps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == kS3Warps) {  // producer warp
+        for (int t = 0; t < n_rel; ++t) {
+            const int b = t & 1;
+            const int k = a.slot_rel[r_begin + t];
+            unsigned char *tile = smem_raw + (size_t)b * tile_bytes;
+            if (lane == 0) {
+                if (t >= 2) mbar_wait(&empty[b], (uint32_t)(((t >> 1) - 1) & 1));
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&full[b], tile_bytes);
+                bulk_load(tile, a.op + ((size_t)p * a.K + k) * a.n_op_rows * 32, tile_bytes, &full[b]);
+            }
+            __syncwarp();
+            mbar_wait(&full[b], (uint32_t)((t >> 1) & 1));
+            if (a.mask != nullptr) {
+                // layer-1 dropout on identity features drops whole operand rows (1/keep is applied to the sums)
+                const int base_bit = k * a.n_op_rows;
+                for (int c = lane; c < a.n_op_rows; c += 32)
+                    if (!mask_bit(a.mask, base_bit + c)) {
+                        float4 *row = reinterpret_cast<float4 *>(tile + ((size_t)c << 7));
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) row[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ready[b]);
+        }
+        return;
+    }
+
+    float4 acc[RPQ];
+#pragma unroll
+    for (int s = 0; s < RPQ; ++s) acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int t = 0; t < n_rel; ++t) {
+        const int k = a.slot_rel[r_begin + t];
+        const int h = __ldg(a.hdr + ((size_t)k * kS3Warps + warp) * 8 + l8);
+        const int4 *__restrict__ ep = a.ent + (size_t)__shfl_sync(kFull, h, 0) * 4 + quarter;
+        prefetch_l1(ep);
+        prefetch_l1(ep + 8);
+        mbar_wait(&ready[t & 1], (uint32_t)((t >> 1) & 1));
+        mbar_wait(&full[t & 1], (uint32_t)((t >> 1) & 1));
+        const unsigned char *xrow = smem_raw + (size_t)(t & 1) * tile_bytes + (l8 << 4);
+        stream_slots<0, RPQ>(acc, h, ep, xrow);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[t & 1]);
+    }
+
+    const float sc = a.mask != nullptr ? a.scale : 1.f;
+#pragma unroll
+    for (int s = 0; s < RPQ; ++s) {
+        const int u = __ldg(a.orow + (warp * a.rpq + s) * 4 + quarter);
+        if (u >= 0)
+            *reinterpret_cast<float4 *>(a.out + (((size_t)slot * a.P + p) * a.n_out_rows + u) * 32 + (l8 << 2)) =
+                make_float4(acc[s].x * sc, acc[s].y * sc, acc[s].z * sc, acc[s].w * sc);
+    }
+}
+
+// Backward products G_k = A_k^T dS for every relation of a group of many small relations: dS (all P
+// panels) stays in shared memory for the whole kernel, each relation's rows come in their own sorted
+// order and are written straight to HBM.  No barrier after the initial load.
+template <int P>
+__global__ void __launch_bounds__(kStagedThreads, 1) spmm_tstaged_kernel(const TaskArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int l8 = lane & 7, quarter = lane >> 3;
+    const int slot = blockIdx.x;
+    const int r_begin = a.slot_ptr[slot], n_rel = a.slot_ptr[slot + 1] - r_begin;
+    const uint32_t panel_bytes = (uint32_t)a.n_op_rows * 128u;
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(a.op);
+        float4 *dst = reinterpret_cast<float4 *>(smem_raw);
+        const int n4 = P * a.n_op_rows * 8;
+        for (int i = threadIdx.x; i < n4; i += kStagedThreads) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const unsigned char *xrow = smem_raw + (l8 << 4);
+    const size_t out_rows = (size_t)a.K * a.n_out_rows;
+
+    for (int t = 0; t < n_rel; ++t) {
+        const int k = a.slot_rel[r_begin + t];
+        const int h = __ldg(a.hdr + ((size_t)k * kTsWarps + warp) * 8 + l8);
+        const int4 *__restrict__ ep = a.ent + (size_t)__shfl_sync(kFull, h, 0) * 4 + quarter;
+        const int *__restrict__ orow = a.orow + (size_t)k * a.orow_stride + warp * a.rpq * 4 + quarter;
+        prefetch_l1(ep);
+        prefetch_l1(ep + 8);
+        for (int s = 0; s < a.rpq; ++s) {
+            const int n2 = task_count(h, s, 0);
+            const int c = __ldg(orow + s * 4);
+            float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+            stream_steps(ep, n2, [&](int off, int vbits) {
+                gather_fma(s0, xrow, off, vbits);
+                if constexpr (P > 1) gather_fma(s1, xrow + panel_bytes, off, vbits);
+                if constexpr (P > 2) gather_fma(s2, xrow + 2 * panel_bytes, off, vbits);
+                if constexpr (P > 2) gather_fma(s3, xrow + 3 * panel_bytes, off, vbits);
+            });
+            const float4 sum[4] = {s0, s1, s2, s3};
+            if (c >= 0) {
+                float sc = 1.f;
+                if (a.mask != nullptr) sc = mask_bit(a.mask, k * a.n_out_rows + c) ? a.scale : 0.f;
+#pragma unroll
+                for (int pp = 0; pp < P; ++pp)
+                    *reinterpret_cast<float4 *>(a.out + ((size_t)pp * out_rows + (size_t)k * a.n_out_rows + c) * 32 + (l8 << 2)) =
+                        make_float4(sum[pp].x * sc, sum[pp].y * sc, sum[pp].z * sc, sum[pp].w * sc);
+            }
+        }
+    }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------ launchers
@@ -344,6 +542,53 @@ void launch_spmm_staged(const StagedArgs &a, cudaStream_t s) {
     else if (rpq <= 6) launch_staged_t<6>(a, s);
     else if (rpq <= 8) launch_staged_t<8>(a, s);
     else DGN_FAIL(DGN_ERR_UNSUPPORTED, "staged spmm: %d rows per quarter-warp", rpq);
+}
+
+bool staged3_supported(int n_i, int n_j, int K) {
+    return K >= 8 && staged_smem_bytes(n_j) <= 200 * 1024 && n_i <= 8 * 4 * kS3Warps;
+}
+
+bool tstaged_supported(int n_i, int n_j, int K, int P) {
+    return K >= 8 && (size_t)P * n_i * 128 <= 200 * 1024 && n_j <= 8 * 4 * kTsWarps && P <= 4;
+}
+
+template <int RPQ>
+static void launch_staged3_t(const TaskArgs &a, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(spmm_staged3_kernel<RPQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    spmm_staged3_kernel<RPQ><<<a.n_slots * a.P, kStagedThreads, staged_smem_bytes(a.n_op_rows), s>>>(a);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_spmm_staged3(const TaskArgs &a, cudaStream_t s) {
+    if (a.rpq <= 2) launch_staged3_t<2>(a, s);
+    else if (a.rpq <= 4) launch_staged3_t<4>(a, s);
+    else if (a.rpq <= 6) launch_staged3_t<6>(a, s);
+    else if (a.rpq <= 8) launch_staged3_t<8>(a, s);
+    else DGN_FAIL(DGN_ERR_UNSUPPORTED, "staged spmm: %d rows per quarter-warp", a.rpq);
+}
+
+template <int P>
+static void launch_tstaged_t(const TaskArgs &a, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(spmm_tstaged_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    spmm_tstaged_kernel<P><<<a.n_slots, kStagedThreads, (size_t)P * a.n_op_rows * 128, s>>>(a);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_spmm_tstaged(const TaskArgs &a, cudaStream_t s) {
+    switch (a.P) {
+        case 1: launch_tstaged_t<1>(a, s); break;
+        case 2: launch_tstaged_t<2>(a, s); break;
+        case 4: launch_tstaged_t<4>(a, s); break;
+        default: DGN_FAIL(DGN_ERR_UNSUPPORTED, "transposed staged spmm: %d panels", a.P);
+    }
 }
 
 }  // namespace dgn
