@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libdecagon_b200.so')
+LIB_PATH = os.environ.get('DGN_LIB_PATH') or os.path.join(_HERE, 'libdecagon_b200.so')  # DGN_LIB_PATH: kernel experiments
 
 DEC_KINDS = {'innerproduct': 0, 'distmult': 1, 'bilinear': 2, 'dedicom': 3}
 LOSS_KINDS = {'hinge': 0, 'xent': 1}

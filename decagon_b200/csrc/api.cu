@@ -100,9 +100,24 @@ SegTable build_segments(const HostCsr &h, int seg_len, bool every_row) {
 struct SlotTable {
     int n_slots = 0;
     int *ptr = nullptr, *rel = nullptr;
+    std::vector<std::vector<int>> lists;  // host copy: relations of every slot, ascending
 };
 
-// longest-processing-time assignment of relations to persistent CTAs, balanced by nnz;
+SlotTable upload_slots(const std::vector<std::vector<int>> &lists) {
+    std::vector<int> ptr(1, 0), rel;
+    for (auto &l : lists) {
+        rel.insert(rel.end(), l.begin(), l.end());
+        ptr.push_back((int)rel.size());
+    }
+    SlotTable t;
+    t.n_slots = (int)lists.size();
+    t.ptr = dev_upload(ptr);
+    t.rel = dev_upload(rel);
+    t.lists = lists;
+    return t;
+}
+
+// longest-processing-time assignment of relations to persistent CTAs, balanced by weight;
 // inside a slot relations stay in ascending order (fixed summation order)
 SlotTable build_slots(const std::vector<long long> &weight, int n_slots) {
     const int K = (int)weight.size();
@@ -120,17 +135,31 @@ SlotTable build_slots(const std::vector<long long> &weight, int n_slots) {
         lists[l.second].push_back(k);
         heap.push(Load(l.first + weight[k], l.second));
     }
-    std::vector<int> ptr(1, 0), rel;
-    for (auto &l : lists) {
-        std::sort(l.begin(), l.end());
-        rel.insert(rel.end(), l.begin(), l.end());
-        ptr.push_back((int)rel.size());
+    for (auto &l : lists) std::sort(l.begin(), l.end());
+    return upload_slots(lists);
+}
+
+// every list of `coarse` cut into `parts` contiguous pieces of about equal weight (the pieces of slot s
+// are slots s * parts .. s * parts + parts - 1): a warp stream laid out for `coarse` is contiguous for
+// the pieces too
+SlotTable split_slots(const SlotTable &coarse, int parts, const std::vector<long long> &weight) {
+    std::vector<std::vector<int>> lists;
+    for (auto &l : coarse.lists) {
+        long long total = 0;
+        for (int k : l) total += weight[k];
+        size_t i = 0;
+        long long done = 0;
+        for (int part = 0; part < parts; ++part) {
+            std::vector<int> piece;
+            const long long target = total * (part + 1) / parts;
+            while (i < l.size() && (part == parts - 1 || done + weight[l[i]] / 2 < target)) {
+                done += weight[l[i]];
+                piece.push_back(l[i++]);
+            }
+            lists.push_back(piece);
+        }
     }
-    SlotTable t;
-    t.n_slots = n_slots;
-    t.ptr = dev_upload(ptr);
-    t.rel = dev_upload(rel);
-    return t;
+    return upload_slots(lists);
 }
 
 // Warp-task streams of the staged v3 kernels (TaskArgs in dgn_internal.cuh)
@@ -138,7 +167,10 @@ struct TaskCsr {
     int n_warps = 0, rpq = 0, orow_stride = 0;
     int *hdr = nullptr, *orow = nullptr;
     int4 *ent = nullptr;
-    std::vector<long long> rel_steps;  // pair-steps of the longest warp stream per relation (load balance weight)
+    // host side, between plan and layout
+    std::vector<int> h_hdr, h_orow;
+    std::vector<long long> rel_steps;     // pair-steps of the longest warp stream per relation (balance weight)
+    std::vector<long long> start;         // [K][n_warps] first pair-step of (k, w) in the laid-out streams
 };
 void free_task(TaskCsr &c) {
     dev_free(c.hdr);
@@ -147,27 +179,24 @@ void free_task(TaskCsr &c) {
     c = TaskCsr();
 }
 
-// rels: K matrices with n_rows rows each.  Rows are sorted by length (summed over the relations, or
-// per relation when per_rel); consecutive groups of 4 go to the n_warps warps in snake order; slot s of
-// warp w is its s-th group.  round_rpq: slots per warp rounded up to an even count (the forward kernel
-// is compiled for 2, 4, 6, 8).
-TaskCsr build_task_csr(const std::vector<HostCsr> &rels, int n_rows, int n_warps, bool per_rel, bool round_rpq) {
+// Step 1: row order, slot counts and the balance weights.  rels: K matrices with n_rows rows each.
+// Rows are sorted by length (summed over the relations, or per relation when per_rel); consecutive
+// groups of 4 go to the n_warps warps in snake order; slot s of warp w is its s-th group.  round_rpq:
+// slots per warp rounded up to an even count (the forward kernel is compiled for 2, 4, 6, 8).
+TaskCsr plan_task_csr(const std::vector<HostCsr> &rels, int n_rows, int n_warps, bool per_rel, bool round_rpq) {
     const int K = (int)rels.size();
     const int n_groups = (n_rows + 3) / 4;
     int rpq = std::max(1, (n_groups + n_warps - 1) / n_warps);
     if (round_rpq) rpq = (rpq + 1) / 2 * 2;
     DGN_REQUIRE(rpq <= 8, "staged spmm: %d rows per quarter-warp (at most 8)", rpq);
-    const int n_slots = n_warps * rpq;  // (warp, slot) pairs
+    const int n_ws = n_warps * rpq;  // (warp, slot) pairs
     TaskCsr out;
-    out.n_warps = n_warps, out.rpq = rpq, out.orow_stride = per_rel ? n_slots * 4 : 0;
+    out.n_warps = n_warps, out.rpq = rpq, out.orow_stride = per_rel ? n_ws * 4 : 0;
     out.rel_steps.assign(K, 0);
-    std::vector<int> hdr((size_t)K * n_warps * 8, 0), orow((size_t)(per_rel ? K : 1) * n_slots * 4, -1);
-    std::vector<int4> ent;
-    long long nnz = 0;
-    for (auto &c : rels) nnz += c.nnz();
-    ent.reserve((size_t)(nnz * 3 / 4 + 1024));
+    out.h_hdr.assign((size_t)K * n_warps * 4, 0);
+    out.h_orow.assign((size_t)(per_rel ? K : 1) * n_ws * 4, -1);
     std::vector<long long> weight((size_t)n_rows, 0);
-    std::vector<int> order((size_t)n_rows), map((size_t)n_slots * 4);
+    std::vector<int> order((size_t)n_rows), map((size_t)n_ws * 4);
     auto make_map = [&]() {  // map[(w * rpq + s) * 4 + quarter] = row
         std::iota(order.begin(), order.end(), 0);
         std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return weight[x] > weight[y]; });
@@ -182,54 +211,89 @@ TaskCsr build_task_csr(const std::vector<HostCsr> &rels, int n_rows, int n_warps
         for (auto &c : rels)
             for (int u = 0; u < n_rows; ++u) weight[u] += c.rowptr[u + 1] - c.rowptr[u];
         make_map();
-        std::copy(map.begin(), map.end(), orow.begin());
+        std::copy(map.begin(), map.end(), out.h_orow.begin());
     }
-    const int4 pad = make_int4(0, 0, 0, 0);
     for (int k = 0; k < K; ++k) {
         const HostCsr &c = rels[k];
         if (per_rel) {
             for (int u = 0; u < n_rows; ++u) weight[u] = c.rowptr[u + 1] - c.rowptr[u];
             make_map();
-            std::copy(map.begin(), map.end(), orow.begin() + (size_t)k * n_slots * 4);
+            std::copy(map.begin(), map.end(), out.h_orow.begin() + (size_t)k * n_ws * 4);
         }
+        const int *m = per_rel ? map.data() : out.h_orow.data();
         for (int w = 0; w < n_warps; ++w) {
-            int *h = hdr.data() + ((size_t)k * n_warps + w) * 8;
-            DGN_REQUIRE(ent.size() / 4 < (size_t)INT32_MAX, "staged spmm: stream offsets overflow int32");
-            h[0] = (int)(ent.size() / 4);
+            int *h = out.h_hdr.data() + ((size_t)k * n_warps + w) * 4;
             long long steps = 0;
             for (int s = 0; s < rpq; ++s) {
                 int cnt = 0;
                 for (int q = 0; q < 4; ++q) {
-                    const int u = map[(size_t)(w * rpq + s) * 4 + q];
+                    const int u = m[(size_t)(w * rpq + s) * 4 + q];
                     if (u >= 0) cnt = std::max(cnt, c.rowptr[u + 1] - c.rowptr[u]);
                 }
                 const int n2 = (cnt + 1) / 2;
                 DGN_REQUIRE(n2 <= 0xffff, "staged spmm: row with %d non-zeros", cnt);
-                h[1 + (s >> 1)] |= n2 << ((s & 1) * 16);
+                h[s >> 1] |= n2 << ((s & 1) * 16);
                 steps += n2;
-                const size_t base = ent.size();
-                ent.resize(base + (size_t)n2 * 4, pad);
-                for (int q = 0; q < 4; ++q) {
-                    const int u = map[(size_t)(w * rpq + s) * 4 + q];
-                    if (u < 0) continue;
-                    const int b = c.rowptr[u], n = c.rowptr[u + 1] - b;
-                    for (int i = 0; i < n; ++i) {
-                        int4 &x = ent[base + (size_t)(i >> 1) * 4 + q];
-                        int bits;
-                        memcpy(&bits, &c.val[b + i], sizeof(float));
-                        if (i & 1) x.z = c.col[b + i] << 7, x.w = bits;
-                        else x.x = c.col[b + i] << 7, x.y = bits;
-                    }
-                }
             }
             out.rel_steps[k] = std::max(out.rel_steps[k], steps);
         }
     }
-    ent.resize(ent.size() + 16, pad);  // the kernels fetch two pair-steps ahead
-    out.hdr = dev_upload(hdr);
-    out.orow = dev_upload(orow);
-    out.ent = dev_upload(ent);
     return out;
+}
+
+// Step 2: the streams, contiguous per (slot of `slots`, warp) over the slot's relations, and the upload.
+void layout_task_csr(TaskCsr &t, const std::vector<HostCsr> &rels, const SlotTable &slots) {
+    const int K = (int)rels.size(), n_warps = t.n_warps, rpq = t.rpq;
+    const int n_ws = n_warps * rpq;
+    long long total = 0;
+    for (int k = 0; k < K; ++k)
+        for (int w = 0; w < n_warps; ++w)
+            for (int s = 0; s < rpq; ++s) total += (t.h_hdr[((size_t)k * n_warps + w) * 4 + (s >> 1)] >> ((s & 1) * 16)) & 0xffff;
+    total += (long long)slots.n_slots * n_warps * 8 + 64;  // alignment of the stream starts + prefetch overrun
+    DGN_REQUIRE(total < (long long)INT32_MAX / 4, "staged spmm: stream offsets overflow int32");
+    std::vector<int4> ent((size_t)total * 4, make_int4(0, 0, 0, 0));
+    t.start.assign((size_t)K * n_warps, 0);
+    long long cursor = 0;  // pair-steps
+    for (auto &list : slots.lists)
+        for (int w = 0; w < n_warps; ++w) {
+            cursor = (cursor + 7) / 8 * 8;
+            for (int k : list) {
+                const HostCsr &c = rels[k];
+                const int *m = t.h_orow.data() + (t.orow_stride ? (size_t)k * n_ws * 4 : 0);
+                t.start[(size_t)k * n_warps + w] = cursor;
+                for (int s = 0; s < rpq; ++s) {
+                    const int n2 = (t.h_hdr[((size_t)k * n_warps + w) * 4 + (s >> 1)] >> ((s & 1) * 16)) & 0xffff;
+                    for (int q = 0; q < 4; ++q) {
+                        const int u = m[(size_t)(w * rpq + s) * 4 + q];
+                        if (u < 0) continue;
+                        const int b = c.rowptr[u], n = c.rowptr[u + 1] - b;
+                        for (int i = 0; i < n; ++i) {
+                            int4 &x = ent[(size_t)(cursor + (i >> 1)) * 4 + q];
+                            int bits;
+                            memcpy(&bits, &c.val[b + i], sizeof(float));
+                            if (i & 1) x.z = c.col[b + i] << 7, x.w = bits;
+                            else x.x = c.col[b + i] << 7, x.y = bits;
+                        }
+                    }
+                    cursor += n2;
+                }
+            }
+        }
+    t.hdr = dev_upload(t.h_hdr);
+    t.orow = dev_upload(t.h_orow);
+    t.ent = dev_upload(ent);
+    t.h_hdr.clear(), t.h_hdr.shrink_to_fit();
+    t.h_orow.clear(), t.h_orow.shrink_to_fit();
+}
+
+// first pair-step of every (slot, warp) stream for a slot table whose lists are contiguous pieces of the
+// lists the streams were laid out for
+int *upload_wstart(const TaskCsr &t, const SlotTable &slots) {
+    std::vector<int> w((size_t)slots.n_slots * t.n_warps, 0);
+    for (int s = 0; s < slots.n_slots; ++s)
+        if (!slots.lists[s].empty())
+            for (int wi = 0; wi < t.n_warps; ++wi) w[(size_t)s * t.n_warps + wi] = (int)t.start[(size_t)slots.lists[s][0] * t.n_warps + wi];
+    return dev_upload(w);
 }
 
 struct NodeType {
@@ -254,6 +318,7 @@ struct Group {
     bool tstaged = false;        // backward products through spmm_tstaged_kernel
     TaskCsr task_fwd, task_bwd;
     SlotTable slots_bwd;
+    int *wstart1 = nullptr, *wstart2 = nullptr, *wstart_bwd = nullptr;
     // parameter arena offsets (floats)
     size_t w1_off = 0, w2_off = 0, glb_off = 0, loc_off = 0, loc_per_rel = 0;
     // work buffers
@@ -344,6 +409,10 @@ void free_group_device(Group &G) {
     dev_free(G.slots_bwd.rel);
     free_task(G.task_fwd);
     free_task(G.task_bwd);
+    dev_free(G.wstart1);
+    dev_free(G.wstart2);
+    dev_free(G.wstart_bwd);
+    G.slots1 = SlotTable(), G.slots2 = SlotTable(), G.slots_bwd = SlotTable();
     float **bufs[] = {&G.part1, &G.part2, &G.Y1, &G.n1, &G.Y2, &G.n2, &G.P2, &G.dS, &G.G2, &G.bwd_partial, &G.dW2part, &G.dHpart};
     for (float **b : bufs) dev_free(*b);
     dev_free(G.mask1);
@@ -412,19 +481,28 @@ void build_group(dgn_graph *g, Group &G) {
     std::vector<long long> w_fwd(K), w_bwd(K);
     for (int k = 0; k < K; ++k) w_fwd[k] = w_bwd[k] = G.rel[k].nnz() + G.rel[k].n_cols;
     if (G.staged && G.staged_version == 3) {
-        G.task_fwd = build_task_csr(G.rel, n_i, kS3Warps, false, true);
+        G.task_fwd = plan_task_csr(G.rel, n_i, kS3Warps, false, true);
         for (int k = 0; k < K; ++k) w_fwd[k] = G.task_fwd.rel_steps[k] + 64;
+        // layer 1 runs P1 panel CTAs per slot, layer 2 one: the layer-2 slots are pieces of the layer-1 slots
+        G.slots1 = build_slots(w_fwd, std::max(1, g->n_sm / P1));
+        G.slots2 = split_slots(G.slots1, P1, w_fwd);
+        layout_task_csr(G.task_fwd, G.rel, G.slots1);
+        G.wstart1 = upload_wstart(G.task_fwd, G.slots1);
+        G.wstart2 = upload_wstart(G.task_fwd, G.slots2);
+    } else if (G.staged) {
+        G.slots1 = build_slots(w_fwd, std::max(1, g->n_sm / P1));
+        G.slots2 = build_slots(w_fwd, g->n_sm);
     }
     if (G.tstaged) {
         std::vector<HostCsr> relt(K);
         for (int k = 0; k < K; ++k) csr_transpose(G.rel[k], relt[k]);
-        G.task_bwd = build_task_csr(relt, n_j, kTsWarps, true, false);
+        G.task_bwd = plan_task_csr(relt, n_j, kTsWarps, true, false);
         for (int k = 0; k < K; ++k) w_bwd[k] = G.task_bwd.rel_steps[k] + 16;
         G.slots_bwd = build_slots(w_bwd, g->n_sm);
+        layout_task_csr(G.task_bwd, relt, G.slots_bwd);
+        G.wstart_bwd = upload_wstart(G.task_bwd, G.slots_bwd);
     }
     if (G.staged) {
-        G.slots1 = build_slots(w_fwd, std::max(1, g->n_sm / P1));
-        G.slots2 = build_slots(w_fwd, g->n_sm);
         G.part1 = dev_alloc<float>((size_t)G.slots1.n_slots * panel_floats(P1, n_i));
         G.part2 = dev_alloc<float>((size_t)G.slots2.n_slots * panel_floats(1, n_i));
     } else {
@@ -473,10 +551,11 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step) {
         }
     }
     auto spmm_fwd = [&](Group &G, const float *op, int P, long long op_rows, float *part, const SlotTable &slots,
-                        const uint32_t *mask) {
+                        const int *wstart, const uint32_t *mask) {
         if (G.staged && G.staged_version == 3) {
             TaskArgs a = {};
             a.hdr = G.task_fwd.hdr, a.ent = G.task_fwd.ent, a.orow = G.task_fwd.orow, a.orow_stride = 0;
+            a.wstart = wstart;
             a.K = G.K, a.n_warps = G.task_fwd.n_warps, a.rpq = G.task_fwd.rpq;
             a.n_out_rows = G.n_i, a.n_op_rows = G.n_j;
             a.op = op, a.P = P;
@@ -525,7 +604,7 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step) {
     for (int gi = 0; gi < g->n_groups; ++gi) {
         Group &G = g->groups[gi];
         PhaseScope ph(g, "spmm_fwd1", gi);
-        spmm_fwd(G, g->params + G.w1_off, P1, (long long)G.K * G.F_j, G.part1, G.slots1, drop ? G.mask1 : nullptr);
+        spmm_fwd(G, g->params + G.w1_off, P1, (long long)G.K * G.F_j, G.part1, G.slots1, G.wstart1, drop ? G.mask1 : nullptr);
     }
     {
         PhaseScope ph(g, "epilogue");
@@ -544,7 +623,7 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step) {
     for (int gi = 0; gi < g->n_groups; ++gi) {
         Group &G = g->groups[gi];
         PhaseScope ph(g, "spmm_fwd2", gi);
-        spmm_fwd(G, G.P2, 1, (long long)G.K * G.n_j, G.part2, G.slots2, nullptr);
+        spmm_fwd(G, G.P2, 1, (long long)G.K * G.n_j, G.part2, G.slots2, G.wstart2, nullptr);
     }
     {
         PhaseScope ph(g, "epilogue");
@@ -561,6 +640,7 @@ void run_backward(dgn_graph *g, float rate) {
         if (G.tstaged) {
             TaskArgs a = {};
             a.hdr = G.task_bwd.hdr, a.ent = G.task_bwd.ent, a.orow = G.task_bwd.orow, a.orow_stride = G.task_bwd.orow_stride;
+            a.wstart = G.wstart_bwd;
             a.K = G.K, a.n_warps = G.task_bwd.n_warps, a.rpq = G.task_bwd.rpq;
             a.n_out_rows = G.n_j, a.n_op_rows = G.n_i;
             a.op = G.dS, a.P = P;

@@ -110,15 +110,16 @@ struct StagedArgs {
 
 // Staged SpMM v3 ("warp-task streams").  The 4 quarter-warps of a warp work on 4 rows in lockstep;
 // rows are sorted by non-zero count (summed over the relations, or per relation) and consecutive
-// groups of 4 are dealt to the warps in snake order, so lockstep rows have similar lengths and every
-// warp gets the same share of the work.  For every (relation k, warp w) the non-zeros are laid out as
-// ONE flat stream the warp reads front to back: slot s (the s-th row group of the warp) contributes
-// cnt(k, w, s) pair-steps, a pair-step is 4 x int4 = one {offset0, value0, offset1, value1} per
-// quarter-warp (offset = byte offset of the operand row in a [rows][32] tile; padding = (0, 0.0f)).
+// groups of 4 are dealt to the warps in snake order; slot s of warp w is its s-th group.  A CTA owns a
+// list of relations (slot table) and every warp w of it reads ONE contiguous stream: for each relation
+// of the list in order, for each slot s, cnt(k, w, s) pair-steps; a pair-step is 4 x int4 = one
+// {offset0, value0, offset1, value1} per quarter-warp (offset = byte offset of the operand row in a
+// [rows][32] tile; padding = (0, 0.0f)).
 struct TaskArgs {
-    const int *hdr;      // [K][n_warps][8]: [0] first pair-step of the stream, [1..4] 8 x uint16 pair-step counts
-    const int4 *ent;     // pair-steps
-    const int *orow;     // result row of (k, w, s, quarter) or -1: [n_warps * rpq * 4] if orow_stride == 0 else [K][...]
+    const int *hdr;      // [K][n_warps][4]: 8 x uint16 pair-step counts of the slots
+    const int4 *ent;     // the streams
+    const int *wstart;   // [n_slots][n_warps]: first pair-step of the warp's stream for this slot table
+    const int *orow;     // result row of (w, s, quarter) or -1: [n_warps * rpq * 4] if orow_stride == 0 else [K][...]
     int orow_stride;
     int K, n_warps, rpq;
     int n_out_rows;      // rows of one relation's result

@@ -291,49 +291,81 @@ __global__ void __launch_bounds__(kStagedThreads, 1) spmm_staged_kernel(const St
 
 
 // ------------------------------------------------------------------------------ staged path v3
-// Warp-task streams (TaskArgs).  The inner loop is LDG.128 (two steps of the stream, fetched two
-// pair-steps ahead) + 2 x (LDS.128 + 4 FFMA): no row pointers, no shuffles, no per-row control
-// beyond one counter.  Forward: operand tiles move through a full / ready / empty mbarrier pipeline
-// run by a dedicated producer warp (TMA bulk copy, then layer-1 dropout = zeroing the dropped operand
-// rows in the tile), there is NO CTA-wide barrier per relation; the row sums of all relations of the
-// CTA stay in registers.
+// Warp-task streams (TaskArgs).  Every warp reads ONE contiguous stream of (offset, value) steps that
+// spans all relations of its CTA.  The stream comes straight from HBM, so it is moved by cp.async
+// through a warp-private 4-stage ring in shared memory (two blocks always in flight per warp, no
+// registers held); the inner loop is LDS.128 (two steps of the stream) + 2 x (LDS.128 of the operand row
+// + 4 FFMA): no row pointers, no shuffles, no per-row control beyond one counter.
+// Forward: operand tiles move through a full / ready / empty mbarrier pipeline run by a dedicated
+// producer warp (TMA bulk copy, then layer-1 dropout = zeroing the dropped operand rows in the tile);
+// there is NO CTA-wide barrier per relation and the row sums of all relations of the CTA stay in
+// registers.
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ int4 ldg_int4(const int4 *p) { return __ldg(p); }
 __device__ __forceinline__ void fma4(float4 &acc, float v, const float4 &x) {
     acc.x = fmaf(v, x.x, acc.x);
     acc.y = fmaf(v, x.y, acc.y);
     acc.z = fmaf(v, x.z, acc.z);
     acc.w = fmaf(v, x.w, acc.w);
 }
-// acc[p] += value * tile_p[row] for one stream step (offset < 0: padding, nothing is read): predicated
-// LDS.128 + FFMA so that the padded quarter-warps of a step neither branch nor cost a shared-memory wavefront
-// one stream step: acc += value * tile[row].  Padding steps carry (offset 0, value 0): they read row 0 and add
-// nothing, so the loop has no predicates or branches.
+// one stream step: acc += value * tile[row].  Padding steps carry (offset 0, value 0): they read row 0 and
+// add nothing, so the loop has no predicates or branches.
 __device__ __forceinline__ void gather_fma(float4 &acc, const unsigned char *xrow, int off, int vbits) {
     fma4(acc, __int_as_float(vbits), *reinterpret_cast<const float4 *>(xrow + off));
 }
-
-__device__ __forceinline__ int task_count(int h, int s, int lane_base) {
-    // uint16 count of slot s: word 1 + s / 2 of the header, held by lane (1 + s / 2) of every quarter-warp
-    return (__shfl_sync(kFull, h, lane_base + 1 + (s >> 1)) >> ((s & 1) * 16)) & 0xffff;
+// uint16 pair-step count of slot s: word s / 2 of the (relation, warp) header, held by lane s / 2
+__device__ __forceinline__ int task_count(int h, int s) {
+    return (__shfl_sync(kFull, h, s >> 1) >> ((s & 1) * 16)) & 0xffff;
 }
 
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+constexpr int kRingStages = 4;
+constexpr int kRingBlockPs = 8;                                  // pair-steps per block
+constexpr int kRingBlockBytes = kRingBlockPs * 64;               // 512 B = 32 lanes x 16 B
+constexpr int kRingBytes = kRingStages * kRingBlockBytes;        // per warp
 
-// n2 pair-steps of a warp stream starting at ep (this quarter-warp's int4 of the first pair-step;
-// consecutive pair-steps are 4 int4 apart).  Four pair-steps per iteration with their loads issued
-// together and the next iteration's lines prefetched into L1.
+struct StreamReader {
+    unsigned char *ring;  // this warp's ring + quarter * 16
+    const int4 *src;      // the warp's stream + lane (what this lane copies)
+    int gi;               // pair-steps consumed
+    int fetched;          // blocks issued
+
+    __device__ __forceinline__ void init(unsigned char *warp_ring, const int4 *stream, int lane) {
+        ring = warp_ring + (lane >> 3) * 16;
+        src = stream + lane;
+        gi = 0;
+        fetched = 0;
+    }
+    // issue the next block (it overwrites the stage of block fetched - 4, which is fully consumed), then
+    // wait until at most two blocks are pending: blocks <= fetched - 3 are complete
+    __device__ __forceinline__ void refill() {
+        const int lane = threadIdx.x & 31;
+        unsigned char *dst = ring - (lane >> 3) * 16 + (fetched & (kRingStages - 1)) * kRingBlockBytes + lane * 16;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src + (size_t)fetched * (kRingBlockPs * 4))
+                     : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        ++fetched;
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+        __syncwarp();
+    }
+    // pair-steps gi .. gi + d are readable afterwards (d < kRingBlockPs)
+    __device__ __forceinline__ void ensure(int d) {
+        while (((gi + d) >> 3) > fetched - 3) refill();
+    }
+    __device__ __forceinline__ int4 load(int j) const {
+        return *reinterpret_cast<const int4 *>(ring + (((gi + j) << 6) & (kRingBytes - 1)));
+    }
+};
+
+// n2 pair-steps of the warp's stream
 template <typename F>
-__device__ __forceinline__ void stream_steps(const int4 *__restrict__ &ep, int n2, F &&step) {
+__device__ __forceinline__ void stream_steps(StreamReader &rd, int n2, F &&step) {
     int ps = 0;
 #pragma unroll 1
     for (; ps + 4 <= n2; ps += 4) {
-        const int4 e0 = ldg_int4(ep), e1 = ldg_int4(ep + 4), e2 = ldg_int4(ep + 8), e3 = ldg_int4(ep + 12);
-        prefetch_l1(ep + 16);
-        prefetch_l1(ep + 24);
-        ep += 16;
+        rd.ensure(3);
+        const int4 e0 = rd.load(0), e1 = rd.load(1), e2 = rd.load(2), e3 = rd.load(3);
+        rd.gi += 4;
         step(e0.x, e0.y), step(e0.z, e0.w);
         step(e1.x, e1.y), step(e1.z, e1.w);
         step(e2.x, e2.y), step(e2.z, e2.w);
@@ -341,18 +373,19 @@ __device__ __forceinline__ void stream_steps(const int4 *__restrict__ &ep, int n
     }
 #pragma unroll 1
     for (; ps < n2; ++ps) {
-        const int4 e0 = ldg_int4(ep);
-        ep += 4;
+        rd.ensure(0);
+        const int4 e0 = rd.load(0);
+        rd.gi += 1;
         step(e0.x, e0.y), step(e0.z, e0.w);
     }
 }
 
-// slots S .. RPQ - 1 of one warp stream (compile-time recursion keeps acc[] in registers)
+// slots S .. RPQ - 1 of one relation (compile-time recursion keeps acc[] in registers)
 template <int S, int RPQ>
-__device__ __forceinline__ void stream_slots(float4 (&acc)[RPQ], int h, const int4 *__restrict__ &ep, const unsigned char *xrow) {
+__device__ __forceinline__ void stream_slots(float4 (&acc)[RPQ], int h, StreamReader &rd, const unsigned char *xrow) {
     if constexpr (S < RPQ) {
-        stream_steps(ep, task_count(h, S, 0), [&](int off, int vbits) { gather_fma(acc[S], xrow, off, vbits); });
-        stream_slots<S + 1, RPQ>(acc, h, ep, xrow);
+        stream_steps(rd, task_count(h, S), [&](int off, int vbits) { gather_fma(acc[S], xrow, off, vbits); });
+        stream_slots<S + 1, RPQ>(acc, h, rd, xrow);
     }
 }
 
@@ -412,19 +445,25 @@ __global__ void __launch_bounds__(kStagedThreads, 1) spmm_staged3_kernel(const T
 #pragma unroll
     for (int s = 0; s < RPQ; ++s) acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
 
+    StreamReader rd;
+    rd.init(smem_raw + 2 * (size_t)tile_bytes + (size_t)warp * kRingBytes,
+            a.ent + (size_t)__ldg(a.wstart + slot * kS3Warps + warp) * 4, lane);
+    int h_next = 0;
+    if (n_rel > 0) {
+        h_next = __ldg(a.hdr + ((size_t)a.slot_rel[r_begin] * kS3Warps + warp) * 4 + (lane & 3));
+        rd.ensure(3);  // three blocks in flight before the first tile is waited for
+    }
     for (int t = 0; t < n_rel; ++t) {
-        const int k = a.slot_rel[r_begin + t];
-        const int h = __ldg(a.hdr + ((size_t)k * kS3Warps + warp) * 8 + l8);
-        const int4 *__restrict__ ep = a.ent + (size_t)__shfl_sync(kFull, h, 0) * 4 + quarter;
-        prefetch_l1(ep);
-        prefetch_l1(ep + 8);
+        const int h = h_next;
+        if (t + 1 < n_rel) h_next = __ldg(a.hdr + ((size_t)a.slot_rel[r_begin + t + 1] * kS3Warps + warp) * 4 + (lane & 3));
         mbar_wait(&ready[t & 1], (uint32_t)((t >> 1) & 1));
         mbar_wait(&full[t & 1], (uint32_t)((t >> 1) & 1));
         const unsigned char *xrow = smem_raw + (size_t)(t & 1) * tile_bytes + (l8 << 4);
-        stream_slots<0, RPQ>(acc, h, ep, xrow);
+        stream_slots<0, RPQ>(acc, h, rd, xrow);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[t & 1]);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 
     const float sc = a.mask != nullptr ? a.scale : 1.f;
 #pragma unroll
@@ -447,6 +486,15 @@ __global__ void __launch_bounds__(kStagedThreads, 1) spmm_tstaged_kernel(const T
     const int slot = blockIdx.x;
     const int r_begin = a.slot_ptr[slot], n_rel = a.slot_ptr[slot + 1] - r_begin;
     const uint32_t panel_bytes = (uint32_t)a.n_op_rows * 128u;
+
+    StreamReader rd;
+    rd.init(smem_raw + (size_t)P * panel_bytes + (size_t)warp * kRingBytes,
+            a.ent + (size_t)__ldg(a.wstart + slot * kTsWarps + warp) * 4, lane);
+    int h_next = 0;
+    if (n_rel > 0) {
+        h_next = __ldg(a.hdr + ((size_t)a.slot_rel[r_begin] * kTsWarps + warp) * 4 + (lane & 3));
+        rd.ensure(3);
+    }
     {
         const float4 *src = reinterpret_cast<const float4 *>(a.op);
         float4 *dst = reinterpret_cast<float4 *>(smem_raw);
@@ -459,16 +507,14 @@ __global__ void __launch_bounds__(kStagedThreads, 1) spmm_tstaged_kernel(const T
 
     for (int t = 0; t < n_rel; ++t) {
         const int k = a.slot_rel[r_begin + t];
-        const int h = __ldg(a.hdr + ((size_t)k * kTsWarps + warp) * 8 + l8);
-        const int4 *__restrict__ ep = a.ent + (size_t)__shfl_sync(kFull, h, 0) * 4 + quarter;
+        const int h = h_next;
         const int *__restrict__ orow = a.orow + (size_t)k * a.orow_stride + warp * a.rpq * 4 + quarter;
-        prefetch_l1(ep);
-        prefetch_l1(ep + 8);
+        if (t + 1 < n_rel) h_next = __ldg(a.hdr + ((size_t)a.slot_rel[r_begin + t + 1] * kTsWarps + warp) * 4 + (lane & 3));
         for (int s = 0; s < a.rpq; ++s) {
-            const int n2 = task_count(h, s, 0);
+            const int n2 = task_count(h, s);
             const int c = __ldg(orow + s * 4);
             float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
-            stream_steps(ep, n2, [&](int off, int vbits) {
+            stream_steps(rd, n2, [&](int off, int vbits) {
                 gather_fma(s0, xrow, off, vbits);
                 if constexpr (P > 1) gather_fma(s1, xrow + panel_bytes, off, vbits);
                 if constexpr (P > 2) gather_fma(s2, xrow + 2 * panel_bytes, off, vbits);
@@ -485,6 +531,7 @@ __global__ void __launch_bounds__(kStagedThreads, 1) spmm_tstaged_kernel(const T
             }
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 }  // namespace
@@ -544,22 +591,24 @@ void launch_spmm_staged(const StagedArgs &a, cudaStream_t s) {
     else DGN_FAIL(DGN_ERR_UNSUPPORTED, "staged spmm: %d rows per quarter-warp", rpq);
 }
 
-bool staged3_supported(int n_i, int n_j, int K) {
-    return K >= 8 && staged_smem_bytes(n_j) <= 200 * 1024 && n_i <= 8 * 4 * kS3Warps;
-}
+constexpr size_t kMaxDynSmem = 227 * 1024 - 256;  // per-CTA limit minus the static barriers
+static size_t staged3_smem(int n_j) { return staged_smem_bytes(n_j) + (size_t)kS3Warps * kRingBytes; }
+static size_t tstaged_smem(int n_i, int P) { return (size_t)P * n_i * 128 + (size_t)kTsWarps * kRingBytes; }
+
+bool staged3_supported(int n_i, int n_j, int K) { return K >= 8 && staged3_smem(n_j) <= kMaxDynSmem && n_i <= 8 * 4 * kS3Warps; }
 
 bool tstaged_supported(int n_i, int n_j, int K, int P) {
-    return K >= 8 && (size_t)P * n_i * 128 <= 200 * 1024 && n_j <= 8 * 4 * kTsWarps && P <= 4;
+    return K >= 8 && tstaged_smem(n_i, P) <= kMaxDynSmem && n_j <= 8 * 4 * kTsWarps && P <= 4;
 }
 
 template <int RPQ>
 static void launch_staged3_t(const TaskArgs &a, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(spmm_staged3_kernel<RPQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(spmm_staged3_kernel<RPQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
         configured = true;
     }
-    spmm_staged3_kernel<RPQ><<<a.n_slots * a.P, kStagedThreads, staged_smem_bytes(a.n_op_rows), s>>>(a);
+    spmm_staged3_kernel<RPQ><<<a.n_slots * a.P, kStagedThreads, staged3_smem(a.n_op_rows), s>>>(a);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -575,10 +624,10 @@ template <int P>
 static void launch_tstaged_t(const TaskArgs &a, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(spmm_tstaged_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(spmm_tstaged_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
         configured = true;
     }
-    spmm_tstaged_kernel<P><<<a.n_slots, kStagedThreads, (size_t)P * a.n_op_rows * 128, s>>>(a);
+    spmm_tstaged_kernel<P><<<a.n_slots, kStagedThreads, tstaged_smem(a.n_op_rows, P), s>>>(a);
     CUDA_CHECK(cudaGetLastError());
 }
 
