@@ -301,6 +301,13 @@ struct NodeType {
     bool feat_set = false, identity = false;
     std::vector<int> row_groups, col_groups;
     float *H = nullptr, *Z = nullptr, *dZ = nullptr, *dA = nullptr;
+    int lane = 0;  // stream lane of the per-type kernels (epilogues, relu backward)
+};
+
+// last writer of a tensor: consumers on the other lane wait for the event
+struct Dep {
+    cudaEvent_t ev = nullptr;
+    int lane = 0;
 };
 
 struct Group {
@@ -313,6 +320,7 @@ struct Group {
     DevCsr relcsr, fwd, bwd;
     SegTable fwd_seg, bwd_seg;
     bool staged = false;
+    int lane = 0;
     SlotTable slots1, slots2;
     int staged_version = 3;      // 2: spmm_staged_kernel, 3: spmm_staged3_kernel (position order, mbarrier pipeline)
     bool tstaged = false;        // backward products through spmm_tstaged_kernel
@@ -347,8 +355,12 @@ struct dgn_graph {
     bool finalized = false;
     bool allow_staged = true, allow_tstaged = true;
     int staged_version = 3;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;   // lane 0: groups of many small relations (staged kernels), decode, Adam
+    cudaStream_t stream2 = nullptr;  // lane 1: the other groups; ordered against lane 0 by events per tensor
     bool own_stream = false;
+    bool two_lanes = true;
+    std::vector<cudaEvent_t> dep_events;  // pool, reused every step
+    size_t dep_next = 0;
     // parameters
     size_t n_params = 0, dec_off = 0;
     float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
@@ -375,21 +387,53 @@ namespace {
 struct PhaseScope {
     dgn_graph *g;
     cudaEvent_t stop = nullptr;
-    PhaseScope(dgn_graph *g_, const char *name, int group = -1) : g(g_) {
+    cudaStream_t st;
+    PhaseScope(dgn_graph *g_, const char *name, int group = -1, int lane = 0) : g(g_) {
+        st = lane == 1 && g->stream2 ? g->stream2 : g->stream;
         if (!g->timing) return;
         Phase p;
         p.name = name;
         if (group >= 0) p.name += "/g" + std::to_string(group);
         CUDA_CHECK(cudaEventCreate(&p.start));
         CUDA_CHECK(cudaEventCreate(&p.stop));
-        CUDA_CHECK(cudaEventRecord(p.start, g->stream));
+        CUDA_CHECK(cudaEventRecord(p.start, st));
         stop = p.stop;
         g->phases.push_back(p);
     }
     ~PhaseScope() {
-        if (stop) cudaEventRecord(stop, g->stream);
+        if (stop) cudaEventRecord(stop, st);
     }
 };
+
+cudaStream_t lane_stream(dgn_graph *g, int lane) { return lane == 1 && g->two_lanes ? g->stream2 : g->stream; }
+// the tensor was just written on `lane`
+void produced(dgn_graph *g, Dep &d, int lane) {
+    if (!g->two_lanes) return;
+    if (g->dep_next == g->dep_events.size()) {
+        cudaEvent_t e;
+        CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        g->dep_events.push_back(e);
+    }
+    d.ev = g->dep_events[g->dep_next++];
+    d.lane = lane;
+    CUDA_CHECK(cudaEventRecord(d.ev, lane_stream(g, lane)));
+}
+// the next kernel on `lane` reads the tensor
+void consume(dgn_graph *g, const Dep &d, int lane) {
+    if (!g->two_lanes || d.ev == nullptr || d.lane == lane) return;
+    CUDA_CHECK(cudaStreamWaitEvent(lane_stream(g, lane), d.ev, 0));
+}
+// lane 0 continues after everything queued on lane 1 (and vice versa when both)
+void join_lanes(dgn_graph *g, bool both) {
+    if (!g->two_lanes) return;
+    Dep d;
+    produced(g, d, 1);
+    consume(g, d, 0);
+    if (both) {
+        produced(g, d, 0);
+        consume(g, d, 1);
+    }
+}
 
 size_t panel_floats(int P, long long rows) { return (size_t)P * (size_t)rows * 32; }
 
@@ -535,16 +579,26 @@ uint32_t dropout_threshold(float rate) {
     return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
 }
 
-void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step) {
+// Per-step dependency state: one Dep per tensor that crosses lanes.
+struct StepDeps {
+    std::vector<Dep> S1, S2, dH;   // per group: layer-1 / layer-2 partial sums, dH partials
+    std::vector<Dep> H, Z, dZ, dA; // per node type
+};
+
+void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step, StepDeps &D) {
     const int P1 = g->P1;
-    cudaStream_t s = g->stream;
     const bool drop = rate > 0.f;
     const float keep = 1.f - rate;
     const float scale = drop ? 1.f / keep : 1.f;
+    D.S1.assign(g->n_groups, Dep()), D.S2.assign(g->n_groups, Dep()), D.dH.assign(g->n_groups, Dep());
+    D.H.assign(g->n_types, Dep()), D.Z.assign(g->n_types, Dep()), D.dZ.assign(g->n_types, Dep()), D.dA.assign(g->n_types, Dep());
+    g->dep_next = 0;
+    join_lanes(g, true);  // lane 1 starts after everything queued so far (previous step's Adam, parameter uploads)
     if (drop) {
-        PhaseScope ph(g, "mask");
         const uint32_t thr = dropout_threshold(rate);
         for (auto &G : g->groups) {
+            PhaseScope ph(g, "mask", -1, G.lane);
+            cudaStream_t s = lane_stream(g, G.lane);
             launch_gen_mask(G.mask1, G.mask1_words, G.F_j, 0, G.r0, kStreamDropout1, step, seed, thr, s);
             launch_gen_mask(G.mask2, G.mask2_words, (long long)G.n_j * g->d1, G.n_j * P1, G.r0, kStreamDropout2, step, seed, thr, s);
             g->launches += 2;
@@ -552,6 +606,7 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step) {
     }
     auto spmm_fwd = [&](Group &G, const float *op, int P, long long op_rows, float *part, const SlotTable &slots,
                         const int *wstart, const uint32_t *mask) {
+        cudaStream_t s = lane_stream(g, G.lane);
         if (G.staged && G.staged_version == 3) {
             TaskArgs a = {};
             a.hdr = G.task_fwd.hdr, a.ent = G.task_fwd.ent, a.orow = G.task_fwd.orow, a.orow_stride = 0;
@@ -591,6 +646,7 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step) {
         DGN_REQUIRE((int)T.row_groups.size() <= kMaxGroupsPerType, "more than %d groups share row type %d", kMaxGroupsPerType, t);
         for (int gi : T.row_groups) {
             Group &G = g->groups[gi];
+            consume(g, layer == 1 ? D.S1[gi] : D.S2[gi], T.lane);
             EpiGroup &eg = e.g[e.n_groups++];
             eg.partial = layer == 1 ? G.part1 : G.part2;
             eg.row_seg_ptr = G.staged ? nullptr : G.fwd_seg.row_seg_ptr;
@@ -598,45 +654,56 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step) {
             eg.Y = layer == 1 ? G.Y1 : G.Y2;
             eg.nrm = layer == 1 ? G.n1 : G.n2;
         }
-        launch_node_epilogue(e, layer == 1 ? P1 : 1, s);
+        PhaseScope ph(g, "epilogue", -1, T.lane);
+        launch_node_epilogue(e, layer == 1 ? P1 : 1, lane_stream(g, T.lane));
         g->launches++;
+        produced(g, layer == 1 ? D.H[t] : D.Z[t], T.lane);
     };
-    for (int gi = 0; gi < g->n_groups; ++gi) {
+    // lane 0 groups first: their kernels are the long ones
+    std::vector<int> order;
+    for (int lane = 0; lane < 2; ++lane)
+        for (int gi = 0; gi < g->n_groups; ++gi)
+            if (g->groups[gi].lane == lane) order.push_back(gi);
+    for (int gi : order) {
         Group &G = g->groups[gi];
-        PhaseScope ph(g, "spmm_fwd1", gi);
-        spmm_fwd(G, g->params + G.w1_off, P1, (long long)G.K * G.F_j, G.part1, G.slots1, G.wstart1, drop ? G.mask1 : nullptr);
+        {
+            PhaseScope ph(g, "spmm_fwd1", gi, G.lane);
+            spmm_fwd(G, g->params + G.w1_off, P1, (long long)G.K * G.F_j, G.part1, G.slots1, G.wstart1, drop ? G.mask1 : nullptr);
+        }
+        produced(g, D.S1[gi], G.lane);
     }
-    {
-        PhaseScope ph(g, "epilogue");
-        for (int t = 0; t < g->n_types; ++t) epilogue(t, 1);
-    }
-    for (int gi = 0; gi < g->n_groups; ++gi) {
+    for (int lane = 0; lane < 2; ++lane)
+        for (int t = 0; t < g->n_types; ++t)
+            if (g->types[t].lane == lane) epilogue(t, 1);
+    for (int gi : order) {
         Group &G = g->groups[gi];
-        PhaseScope ph(g, "project", gi);
-        DenseArgs a = {};
-        a.H = g->types[G.j].H, a.W2 = g->params + G.w2_off, a.P2 = G.P2;
-        a.mask = drop ? G.mask2 : nullptr, a.scale = scale, a.K = G.K, a.n_j = G.n_j;
-        a.n_rb = G.n_rb, a.n_slots = G.slots_proj;
-        launch_project(a, g->d1, g->d2, s);
-        g->launches++;
+        consume(g, D.H[G.j], G.lane);
+        {
+            PhaseScope ph(g, "project", gi, G.lane);
+            DenseArgs a = {};
+            a.H = g->types[G.j].H, a.W2 = g->params + G.w2_off, a.P2 = G.P2;
+            a.mask = drop ? G.mask2 : nullptr, a.scale = scale, a.K = G.K, a.n_j = G.n_j;
+            a.n_rb = G.n_rb, a.n_slots = G.slots_proj;
+            launch_project(a, g->d1, g->d2, lane_stream(g, G.lane));
+            g->launches++;
+        }
+        {
+            PhaseScope ph(g, "spmm_fwd2", gi, G.lane);
+            spmm_fwd(G, G.P2, 1, (long long)G.K * G.n_j, G.part2, G.slots2, G.wstart2, nullptr);
+        }
+        produced(g, D.S2[gi], G.lane);
     }
-    for (int gi = 0; gi < g->n_groups; ++gi) {
-        Group &G = g->groups[gi];
-        PhaseScope ph(g, "spmm_fwd2", gi);
-        spmm_fwd(G, G.P2, 1, (long long)G.K * G.n_j, G.part2, G.slots2, G.wstart2, nullptr);
-    }
-    {
-        PhaseScope ph(g, "epilogue");
-        for (int t = 0; t < g->n_types; ++t) epilogue(t, 2);
-    }
+    for (int lane = 0; lane < 2; ++lane)
+        for (int t = 0; t < g->n_types; ++t)
+            if (g->types[t].lane == lane) epilogue(t, 2);
 }
 
-void run_backward(dgn_graph *g, float rate) {
+void run_backward(dgn_graph *g, float rate, StepDeps &D) {
     const int P1 = g->P1;
-    cudaStream_t s = g->stream;
     const bool drop = rate > 0.f;
     const float scale = drop ? 1.f / (1.f - rate) : 1.f;
     auto spmm_bwd = [&](Group &G, int P, float *out, long long out_rows, const uint32_t *row_mask) {
+        cudaStream_t s = lane_stream(g, G.lane);
         if (G.tstaged) {
             TaskArgs a = {};
             a.hdr = G.task_bwd.hdr, a.ent = G.task_bwd.ent, a.orow = G.task_bwd.orow, a.orow_stride = G.task_bwd.orow_stride;
@@ -664,17 +731,24 @@ void run_backward(dgn_graph *g, float rate) {
             g->launches++;
         }
     };
+    std::vector<int> order;
+    for (int lane = 0; lane < 2; ++lane)
+        for (int gi = 0; gi < g->n_groups; ++gi)
+            if (g->groups[gi].lane == lane) order.push_back(gi);
     // ---- layer 2
-    for (int gi = 0; gi < g->n_groups; ++gi) {
+    for (int gi : order) {
         Group &G = g->groups[gi];
+        cudaStream_t s = lane_stream(g, G.lane);
+        consume(g, D.dZ[G.i], G.lane);
+        consume(g, D.H[G.j], G.lane);
         {
-            PhaseScope ph(g, "epilogue");
+            PhaseScope ph(g, "epilogue", -1, G.lane);
             L2BwdArgs l = {G.Y2, G.n2, g->types[G.i].dZ, G.dS, G.n_i};
             launch_l2norm_bwd(l, 1, s);
             g->launches++;
         }
         {
-            PhaseScope ph(g, "spmm_bwd2", gi);
+            PhaseScope ph(g, "spmm_bwd2", gi, G.lane);
             spmm_bwd(G, 1, G.G2, (long long)G.K * G.n_j, nullptr);
         }
         DenseArgs a = {};
@@ -684,7 +758,7 @@ void run_backward(dgn_graph *g, float rate) {
         a.dW2 = G.n_rb > 1 ? G.dW2part : g->grads + G.w2_off;
         a.dHpart = G.dHpart;
         {
-            PhaseScope ph(g, "dw2", gi);
+            PhaseScope ph(g, "dw2", gi, G.lane);
             a.n_slots = G.slots_proj;
             launch_dw2(a, g->d1, g->d2, s);
             g->launches++;
@@ -693,39 +767,48 @@ void run_backward(dgn_graph *g, float rate) {
                 g->launches++;
             }
         }
-        PhaseScope ph(g, "dh", gi);
-        a.n_slots = G.slots_dh;
-        launch_dh(a, g->d1, g->d2, s);
-        g->launches++;
+        {
+            PhaseScope ph(g, "dh", gi, G.lane);
+            a.n_slots = G.slots_dh;
+            launch_dh(a, g->d1, g->d2, s);
+            g->launches++;
+        }
+        produced(g, D.dH[gi], G.lane);
     }
-    {
-        PhaseScope ph(g, "epilogue");
+    for (int lane = 0; lane < 2; ++lane)
         for (int t = 0; t < g->n_types; ++t) {
             NodeType &T = g->types[t];
+            if (T.lane != lane) continue;
             ReluBwdArgs r = {};
             r.n_rows = T.n;
             r.H = T.H, r.dA = T.dA;
+            consume(g, D.H[t], T.lane);
             for (int gi : T.col_groups) {
+                consume(g, D.dH[gi], T.lane);
                 r.g[r.n_groups].part = g->groups[gi].dHpart;
                 r.g[r.n_groups].n_chunks = g->groups[gi].slots_dh;
                 r.n_groups++;
             }
-            launch_relu_bwd(r, P1, s);
+            PhaseScope ph(g, "epilogue", -1, T.lane);
+            launch_relu_bwd(r, P1, lane_stream(g, T.lane));
             g->launches++;
+            produced(g, D.dA[t], T.lane);
         }
-    }
     // ---- layer 1
-    for (int gi = 0; gi < g->n_groups; ++gi) {
+    for (int gi : order) {
         Group &G = g->groups[gi];
+        cudaStream_t s = lane_stream(g, G.lane);
+        consume(g, D.dA[G.i], G.lane);
         {
-            PhaseScope ph(g, "epilogue");
+            PhaseScope ph(g, "epilogue", -1, G.lane);
             L2BwdArgs l = {G.Y1, G.n1, g->types[G.i].dA, G.dS, G.n_i};
             launch_l2norm_bwd(l, P1, s);
             g->launches++;
         }
-        PhaseScope ph(g, "spmm_bwd1", gi);
+        PhaseScope ph(g, "spmm_bwd1", gi, G.lane);
         spmm_bwd(G, P1, g->grads + G.w1_off, (long long)G.K * G.F_j, drop ? G.mask1 : nullptr);
     }
+    join_lanes(g, false);
 }
 
 // logical [K][rows][32 P] row-major <-> device [P][K * rows][32]
@@ -940,7 +1023,12 @@ extern "C" int dgn_graph_create(dgn_graph **out, int device, int n_types, const 
     CUDA_CHECK(cudaMemset(g->grads, 0, off * sizeof(float)));
     CUDA_CHECK(cudaMemset(g->adam_m, 0, off * sizeof(float)));
     CUDA_CHECK(cudaMemset(g->adam_v, 0, off * sizeof(float)));
-    CUDA_CHECK(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_CHECK(cudaStreamCreateWithPriority(&g->stream, cudaStreamNonBlocking, hi));
+        CUDA_CHECK(cudaStreamCreateWithPriority(&g->stream2, cudaStreamNonBlocking, lo));
+    }
     g->own_stream = true;
     for (int i = 0; i < dgn_graph::kRing; ++i) CUDA_CHECK(cudaEventCreateWithFlags(&g->ring_ev[i], cudaEventDisableTiming));
     g->loss_dev = dev_alloc<float>(1);
@@ -957,6 +1045,8 @@ extern "C" int dgn_graph_create(dgn_graph **out, int device, int n_types, const 
     g->allow_staged = !(env && env[0] == '1');
     env = getenv("DGN_STAGED_VERSION");
     if (env && env[0] == '2') g->staged_version = 2;
+    env = getenv("DGN_SINGLE_STREAM");
+    g->two_lanes = !(env && env[0] == '1');
     env = getenv("DGN_DISABLE_TSTAGED");
     g->allow_tstaged = !(env && env[0] == '1');
     *out = g.release();
@@ -998,7 +1088,9 @@ extern "C" int dgn_graph_destroy(dgn_graph *g) {
         cudaEventDestroy(p.start);
         cudaEventDestroy(p.stop);
     }
+    for (auto &e : g->dep_events) cudaEventDestroy(e);
     if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
+    if (g->stream2) cudaStreamDestroy(g->stream2);
     delete g;
     DGN_API_END
 }
@@ -1068,6 +1160,17 @@ extern "C" int dgn_graph_finalize(dgn_graph *g) {
     }
     CUDA_CHECK(cudaStreamSynchronize(g->stream));
     for (auto &G : g->groups) build_group(g, G);
+    // stream lanes: the groups of many small relations (persistent one-CTA-per-SM kernels) on lane 0, the
+    // rest on lane 1 so that their short kernels fill the gaps; per-type kernels follow their row groups
+    bool any_staged = false;
+    for (auto &G : g->groups) any_staged = any_staged || G.staged;
+    for (auto &G : g->groups) G.lane = (g->two_lanes && any_staged && !G.staged) ? 1 : 0;
+    for (auto &T : g->types) {
+        T.lane = 1;
+        for (int gi : T.row_groups)
+            if (g->groups[gi].lane == 0) T.lane = 0;
+        if (!g->two_lanes || !any_staged) T.lane = 0;
+    }
     g->finalized = true;
     DGN_API_END
 }
@@ -1150,7 +1253,9 @@ extern "C" int dgn_encoder_forward(dgn_graph *g, float dropout, uint64_t seed, u
     check_finalized(g);
     DGN_REQUIRE(dropout >= 0.f && dropout < 1.f, "dropout rate %g outside [0, 1)", dropout);
     CUDA_CHECK(cudaSetDevice(g->device));
-    run_forward(g, dropout, seed, step);
+    StepDeps deps;
+    run_forward(g, dropout, seed, step, deps);
+    join_lanes(g, false);
     DGN_API_END
 }
 
@@ -1186,9 +1291,11 @@ extern "C" int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t
     }
     CUDA_CHECK(cudaEventRecord(g->ring_ev[slot], s));
 
-    run_forward(g, dropout, seed, step);
+    StepDeps deps;
+    run_forward(g, dropout, seed, step, deps);
 
     {
+        for (int t = 0; t < g->n_types; ++t) consume(g, deps.Z[t], 0);
         PhaseScope ph(g, "decode");
         for (auto &T : g->types) CUDA_CHECK(cudaMemsetAsync(T.dZ, 0, panel_floats(1, T.n) * sizeof(float), s));
         if (g->n_params > g->dec_off)
@@ -1208,9 +1315,10 @@ extern "C" int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t
         launch_decode(a, s);
         g->launches++;
         g->last_B = batch_size;
+        for (int t = 0; t < g->n_types; ++t) produced(g, deps.dZ[t], 0);
     }
 
-    run_backward(g, dropout);
+    run_backward(g, dropout, deps);
 
     if (apply_update) {
         PhaseScope ph(g, "adam");
