@@ -359,6 +359,7 @@ struct dgn_graph {
     cudaStream_t stream2 = nullptr;  // lane 1: the other groups; ordered against lane 0 by events per tensor
     bool own_stream = false;
     bool two_lanes = true;
+    bool fuse_adam = true;  // Adam of the layer-1 weights inside the kernel that produces their gradient
     std::vector<cudaEvent_t> dep_events;  // pool, reused every step
     size_t dep_next = 0;
     // parameters
@@ -698,11 +699,15 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step, StepDep
             if (g->types[t].lane == lane) epilogue(t, 2);
 }
 
-void run_backward(dgn_graph *g, float rate, StepDeps &D) {
+struct AdamStep {  // valid (alpha != 0) when the update may be fused into the kernels that produce the gradients
+    float alpha = 0.f, omb1 = 0.f, omb2 = 0.f, eps = 0.f;
+};
+
+void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam) {
     const int P1 = g->P1;
     const bool drop = rate > 0.f;
     const float scale = drop ? 1.f / (1.f - rate) : 1.f;
-    auto spmm_bwd = [&](Group &G, int P, float *out, long long out_rows, const uint32_t *row_mask) {
+    auto spmm_bwd = [&](Group &G, int P, float *out, long long out_rows, const uint32_t *row_mask, bool fuse_adam) {
         cudaStream_t s = lane_stream(g, G.lane);
         if (G.tstaged) {
             TaskArgs a = {};
@@ -713,6 +718,11 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D) {
             a.op = G.dS, a.P = P;
             a.slot_ptr = G.slots_bwd.ptr, a.slot_rel = G.slots_bwd.rel, a.n_slots = G.slots_bwd.n_slots;
             a.out = out, a.mask = row_mask, a.scale = scale;
+            if (fuse_adam) {
+                const size_t off = (size_t)(out - g->grads);
+                a.adam_p = g->params + off, a.adam_m = g->adam_m + off, a.adam_v = g->adam_v + off;
+                a.alpha = adam.alpha, a.omb1 = adam.omb1, a.omb2 = adam.omb2, a.eps = adam.eps;
+            }
             launch_spmm_tstaged(a, s);
             g->launches++;
             return;
@@ -749,7 +759,7 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D) {
         }
         {
             PhaseScope ph(g, "spmm_bwd2", gi, G.lane);
-            spmm_bwd(G, 1, G.G2, (long long)G.K * G.n_j, nullptr);
+            spmm_bwd(G, 1, G.G2, (long long)G.K * G.n_j, nullptr, false);
         }
         DenseArgs a = {};
         a.H = g->types[G.j].H, a.W2 = g->params + G.w2_off, a.G2 = G.G2;
@@ -806,7 +816,7 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D) {
             g->launches++;
         }
         PhaseScope ph(g, "spmm_bwd1", gi, G.lane);
-        spmm_bwd(G, P1, g->grads + G.w1_off, (long long)G.K * G.F_j, drop ? G.mask1 : nullptr);
+        spmm_bwd(G, P1, g->grads + G.w1_off, (long long)G.K * G.F_j, drop ? G.mask1 : nullptr, adam.alpha != 0.f && G.tstaged && g->fuse_adam);
     }
     join_lanes(g, false);
 }
@@ -1045,6 +1055,8 @@ extern "C" int dgn_graph_create(dgn_graph **out, int device, int n_types, const 
     g->allow_staged = !(env && env[0] == '1');
     env = getenv("DGN_STAGED_VERSION");
     if (env && env[0] == '2') g->staged_version = 2;
+    env = getenv("DGN_FUSE_ADAM");
+    g->fuse_adam = !(env && env[0] == '0');
     env = getenv("DGN_SINGLE_STREAM");
     g->two_lanes = !(env && env[0] == '1');
     env = getenv("DGN_DISABLE_TSTAGED");
@@ -1318,14 +1330,31 @@ extern "C" int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t
         for (int t = 0; t < g->n_types; ++t) produced(g, deps.dZ[t], 0);
     }
 
-    run_backward(g, dropout, deps);
+    AdamStep adam;
+    if (apply_update) {
+        // TF 1.8 ApplyAdam: alpha = lr * sqrt(1 - beta2^t) / (1 - beta1^t), float32
+        adam.alpha = learning_rate * sqrtf(1.f - g->b2p) / (1.f - g->b1p);
+        adam.omb1 = 1.f - g->beta1, adam.omb2 = 1.f - g->beta2, adam.eps = g->eps;
+    }
+    run_backward(g, dropout, deps, adam);
 
     if (apply_update) {
         PhaseScope ph(g, "adam");
-        // TF 1.8 ApplyAdam: alpha = lr * sqrt(1 - beta2^t) / (1 - beta1^t), float32
-        const float alpha = learning_rate * sqrtf(1.f - g->b2p) / (1.f - g->b1p);
-        launch_adam(g->params, g->grads, g->adam_m, g->adam_v, (long long)g->n_params, alpha, 1.f - g->beta1, 1.f - g->beta2, g->eps, s);
-        g->launches++;
+        // every variable whose update was not fused into the kernel that produced its gradient
+        size_t begin = 0;
+        auto flush = [&](size_t end) {
+            if (end > begin) {
+                launch_adam(g->params + begin, g->grads + begin, g->adam_m + begin, g->adam_v + begin, (long long)(end - begin),
+                            adam.alpha, adam.omb1, adam.omb2, adam.eps, s);
+                g->launches++;
+            }
+        };
+        for (auto &Gq : g->groups)
+            if (Gq.tstaged && g->fuse_adam && adam.alpha != 0.f) {
+                flush(Gq.w1_off);
+                begin = Gq.w1_off + (size_t)Gq.K * Gq.F_j * g->d1;
+            }
+        flush(g->n_params);
         g->b1p *= g->beta1;
         g->b2p *= g->beta2;
     }

@@ -131,6 +131,10 @@ struct TaskArgs {
     float *out;          // forward: partial [n_slots][P][n_out_rows][32];  backward: [P][K * n_out_rows][32]
     const uint32_t *mask;  // forward: bit k * n_op_rows + operand row;  backward: bit k * n_out_rows + result row
     float scale;
+    // backward only: TF1 Adam applied to the rows as they are produced (out is then not written);
+    // p / m / v have the layout of out
+    float *adam_p, *adam_m, *adam_v;
+    float alpha, omb1, omb2, eps;
 };
 
 struct EpiGroup {

@@ -319,6 +319,8 @@ __device__ __forceinline__ int task_count(int h, int s) {
     return (__shfl_sync(kFull, h, s >> 1) >> ((s & 1) * 16)) & 0xffff;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 constexpr int kRingStages = 4;
 constexpr int kRingBlockPs = 8;                                  // pair-steps per block
 constexpr int kRingBlockBytes = kRingBlockPs * 64;               // 512 B = 32 lanes x 16 B
@@ -513,6 +515,16 @@ __global__ void __launch_bounds__(kStagedThreads, 1) spmm_tstaged_kernel(const T
         for (int s = 0; s < a.rpq; ++s) {
             const int n2 = task_count(h, s);
             const int c = __ldg(orow + s * 4);
+            if (a.adam_p != nullptr && c >= 0) {
+                // the optimizer state of this row is needed right after the gather: start moving it to L2
+#pragma unroll
+                for (int pp = 0; pp < P; ++pp) {
+                    const size_t o = ((size_t)pp * out_rows + (size_t)k * a.n_out_rows + c) * 32 + (l8 << 2);
+                    prefetch_l2(a.adam_p + o);
+                    prefetch_l2(a.adam_m + o);
+                    prefetch_l2(a.adam_v + o);
+                }
+            }
             float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
             stream_steps(rd, n2, [&](int off, int vbits) {
                 gather_fma(s0, xrow, off, vbits);
@@ -525,9 +537,28 @@ __global__ void __launch_bounds__(kStagedThreads, 1) spmm_tstaged_kernel(const T
                 float sc = 1.f;
                 if (a.mask != nullptr) sc = mask_bit(a.mask, k * a.n_out_rows + c) ? a.scale : 0.f;
 #pragma unroll
-                for (int pp = 0; pp < P; ++pp)
-                    *reinterpret_cast<float4 *>(a.out + ((size_t)pp * out_rows + (size_t)k * a.n_out_rows + c) * 32 + (l8 << 2)) =
-                        make_float4(sum[pp].x * sc, sum[pp].y * sc, sum[pp].z * sc, sum[pp].w * sc);
+                for (int pp = 0; pp < P; ++pp) {
+                    const size_t o = ((size_t)pp * out_rows + (size_t)k * a.n_out_rows + c) * 32 + (l8 << 2);
+                    const float4 gr = make_float4(sum[pp].x * sc, sum[pp].y * sc, sum[pp].z * sc, sum[pp].w * sc);
+                    if (a.adam_p == nullptr) {
+                        *reinterpret_cast<float4 *>(a.out + o) = gr;
+                    } else {
+                        // TF 1.8 ApplyAdam, the same arithmetic as adam_kernel (node.cu)
+                        float4 P4 = *reinterpret_cast<const float4 *>(a.adam_p + o), M4 = *reinterpret_cast<const float4 *>(a.adam_m + o);
+                        float4 V4 = *reinterpret_cast<const float4 *>(a.adam_v + o);
+                        const float gg[4] = {gr.x, gr.y, gr.z, gr.w};
+                        float *pq = &P4.x, *mq = &M4.x, *vq = &V4.x;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            mq[q] += (gg[q] - mq[q]) * a.omb1;
+                            vq[q] += (gg[q] * gg[q] - vq[q]) * a.omb2;
+                            pq[q] -= (mq[q] * a.alpha) / (sqrtf(vq[q]) + a.eps);
+                        }
+                        *reinterpret_cast<float4 *>(a.adam_p + o) = P4;
+                        *reinterpret_cast<float4 *>(a.adam_m + o) = M4;
+                        *reinterpret_cast<float4 *>(a.adam_v + o) = V4;
+                    }
+                }
             }
         }
     }

@@ -137,7 +137,9 @@ int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t batch_size
 
 /* optimizer.outputs / neg_outputs / neg_samples of the last dgn_train_step (optimizer.py:49-57) */
 int dgn_last_batch_outputs(dgn_graph *g, float *pos_out, float *neg_out, int64_t *neg_samples_out, int32_t batch_size);
-/* gradient of the last step for one variable (optimizer.grads_vars, optimizer.py:114) */
+/* gradient of the last step for one variable (optimizer.grads_vars, optimizer.py:114).  Only a step run
+ * with apply_update == 0 materialises every gradient: with apply_update != 0 the Adam update of the
+ * layer-1 weights of the many-relation groups is fused into the kernel that produces their gradient. */
 int dgn_grads_get(dgn_graph *g, int kind, int group, int k, float *values_out, int64_t n);
 
 /* optimizer.predictions (optimizer.py:87-106): Z_i loc glb loc Z_j^T of relation r from the
