@@ -66,6 +66,11 @@ SIGNATURES = {
     'dgn_timer_start': (ctypes.c_int, [c_graph]),
     'dgn_timer_stop': (ctypes.c_int, [c_graph, c_f64p]),
     'dgn_memory_bytes': (ctypes.c_int, [c_graph, c_i64p, c_i64p]),
+    'dgn_comm_init': (ctypes.c_int, [c_graph, ctypes.c_int, ctypes.c_int]),
+    'dgn_comm_handle': (ctypes.c_int, [c_graph, ctypes.c_void_p]),
+    'dgn_comm_connect': (ctypes.c_int, [c_graph, ctypes.c_void_p]),
+    'dgn_relation_owner': (ctypes.c_int, [c_graph, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
+    'dgn_partition_relations': (ctypes.c_int, [c_i64p, ctypes.c_int32, ctypes.c_int32, c_i32p]),
 }
 
 
@@ -133,6 +138,14 @@ def csr_from_coo(n_rows, n_cols, rows, cols, vals):
                                   ptr(vals, ctypes.c_float), ptr(rowptr, ctypes.c_int32), ptr(col, ctypes.c_int32),
                                   ptr(val, ctypes.c_float)))
     return rowptr, col, val
+
+
+def partition_relations(weights, world):
+    """Host-only: owner rank of every relation (longest-processing-time, the library's own rule)."""
+    w = np.ascontiguousarray(weights, dtype=np.int64)
+    out = np.empty(len(w), dtype=np.int32)
+    check(load().dgn_partition_relations(ptr(w, ctypes.c_int64), len(w), int(world), ptr(out, ctypes.c_int32)))
+    return out
 
 
 def sampler_thresholds(degrees):

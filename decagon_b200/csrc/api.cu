@@ -301,6 +301,7 @@ struct NodeType {
     bool feat_set = false, identity = false;
     std::vector<int> row_groups, col_groups;
     float *H = nullptr, *Z = nullptr, *dZ = nullptr, *dA = nullptr;
+    long long *dZq = nullptr;  // dZ accumulated by the decode kernel in fixed point
     int lane = 0;  // stream lane of the per-type kernels (epilogues, relu backward)
 };
 
@@ -312,6 +313,18 @@ struct Dep {
 
 struct Group {
     int i = 0, j = 0, K = 0, decoder = 0, r0 = 0;
+    // multi-GPU: the relations of a group of many small relations are partitioned over the ranks; Kl of
+    // the K relations live here (loc: their group-wide indices, ascending; loc_index: inverse or -1).
+    // Encoder state (adjacency, W1, W2, masks) is sized by Kl; decoder variables are replicated (K).
+    bool partitioned = false;
+    int Kl = 0;
+    std::vector<int> loc, loc_index, owner;
+    int *rel_ids = nullptr;  // device: flat relation id of every local relation (dropout streams are keyed by it)
+    struct Exchange {        // partial sums that every rank needs from every rank: S1, S2, dH
+        int id = -1;
+        size_t floats = 0, off = 0;  // two parity buffers of `floats` at byte offset off of the comm arena
+        uint32_t stamp = 0;
+    } xch[3];
     int n_i = 0, n_j = 0, F_j = 0;
     std::vector<HostCsr> rel;
     std::vector<bool> rel_set;
@@ -358,6 +371,15 @@ struct dgn_graph {
     cudaStream_t stream = nullptr;   // lane 0: groups of many small relations (staged kernels), decode, Adam
     cudaStream_t stream2 = nullptr;  // lane 1: the other groups; ordered against lane 0 by events per tensor
     bool own_stream = false;
+    int rank = 0, world = 1;
+    bool arena_ready = false;
+    // multi-GPU exchange arena: [flags: kMaxWorld x kMaxExchanges uint32][buffers]; peers map it through CUDA IPC
+    unsigned char *comm = nullptr;
+    size_t comm_bytes = 0;
+    unsigned char *peer_comm[kMaxWorld] = {};
+    uint32_t **peer_flags_dev = nullptr;
+    bool connected = false;
+    int n_exchanges = 0;
     bool two_lanes = true;
     bool fuse_adam = true;  // Adam of the layer-1 weights inside the kernel that produces their gradient
     std::vector<cudaEvent_t> dep_events;  // pool, reused every step
@@ -458,6 +480,7 @@ void free_group_device(Group &G) {
     dev_free(G.wstart2);
     dev_free(G.wstart_bwd);
     G.slots1 = SlotTable(), G.slots2 = SlotTable(), G.slots_bwd = SlotTable();
+    dev_free(G.rel_ids);
     float **bufs[] = {&G.part1, &G.part2, &G.Y1, &G.n1, &G.Y2, &G.n2, &G.P2, &G.dS, &G.G2, &G.bwd_partial, &G.dW2part, &G.dHpart};
     for (float **b : bufs) dev_free(*b);
     dev_free(G.mask1);
@@ -466,9 +489,20 @@ void free_group_device(Group &G) {
 
 void build_group(dgn_graph *g, Group &G) {
     free_group_device(G);
-    const int K = G.K, n_i = G.n_i, n_j = G.n_j, P1 = g->P1;
+    const int K = G.Kl, n_i = G.n_i, n_j = G.n_j, P1 = g->P1;  // K: the LOCAL relations from here on
+    std::vector<HostCsr> local_copy;
+    if (G.partitioned) {
+        local_copy.reserve(K);
+        for (int k : G.loc) local_copy.push_back(G.rel[k]);
+    }
+    const std::vector<HostCsr> &rel = G.partitioned ? local_copy : G.rel;
+    {
+        std::vector<int> ids((size_t)K + 1, 0);  // + 1: the packed layer-1 mask rounds its bit count up to a word
+        for (int l = 0; l < K; ++l) ids[l] = G.r0 + G.loc[l];
+        G.rel_ids = dev_upload(ids);
+    }
     G.nnz = 0;
-    for (auto &c : G.rel) G.nnz += c.nnz();
+    for (auto &c : rel) G.nnz += c.nnz();
     DGN_REQUIRE(G.nnz < (long long)INT32_MAX, "group (%d,%d): %lld non-zeros do not fit int32 offsets", G.i, G.j, G.nnz);
     DGN_REQUIRE((long long)K * std::max(n_j, G.F_j) < (long long)INT32_MAX / 64, "group (%d,%d): K * n_j too large", G.i, G.j);
 
@@ -479,9 +513,9 @@ void build_group(dgn_graph *g, Group &G) {
     cat_rel.val.reserve((size_t)G.nnz);
     for (int k = 0; k < K; ++k) {
         const int base = (int)cat_rel.col.size();
-        for (int u = 0; u <= n_i; ++u) cat_rel.rowptr.push_back(base + G.rel[k].rowptr[u]);
-        cat_rel.col.insert(cat_rel.col.end(), G.rel[k].col.begin(), G.rel[k].col.end());
-        cat_rel.val.insert(cat_rel.val.end(), G.rel[k].val.begin(), G.rel[k].val.end());
+        for (int u = 0; u <= n_i; ++u) cat_rel.rowptr.push_back(base + rel[k].rowptr[u]);
+        cat_rel.col.insert(cat_rel.col.end(), rel[k].col.begin(), rel[k].col.end());
+        cat_rel.val.insert(cat_rel.val.end(), rel[k].val.begin(), rel[k].val.end());
     }
     cat_rel.n_rows = K * (n_i + 1) - 1;
     G.relcsr = upload_csr(cat_rel);
@@ -492,7 +526,7 @@ void build_group(dgn_graph *g, Group &G) {
     fwd.n_cols = K * n_j;
     fwd.rowptr.assign((size_t)n_i + 1, 0);
     for (int k = 0; k < K; ++k)
-        for (int u = 0; u < n_i; ++u) fwd.rowptr[(size_t)u + 1] += G.rel[k].rowptr[u + 1] - G.rel[k].rowptr[u];
+        for (int u = 0; u < n_i; ++u) fwd.rowptr[(size_t)u + 1] += rel[k].rowptr[u + 1] - rel[k].rowptr[u];
     for (int u = 0; u < n_i; ++u) fwd.rowptr[u + 1] += fwd.rowptr[u];
     fwd.col.resize((size_t)G.nnz);
     fwd.val.resize((size_t)G.nnz);
@@ -500,17 +534,17 @@ void build_group(dgn_graph *g, Group &G) {
         std::vector<int> cursor(fwd.rowptr.begin(), fwd.rowptr.end() - 1);
         for (int k = 0; k < K; ++k)
             for (int u = 0; u < n_i; ++u)
-                for (int e = G.rel[k].rowptr[u]; e < G.rel[k].rowptr[u + 1]; ++e) {
+                for (int e = rel[k].rowptr[u]; e < rel[k].rowptr[u + 1]; ++e) {
                     const int dst = cursor[u]++;
-                    fwd.col[dst] = k * n_j + G.rel[k].col[e];
-                    fwd.val[dst] = G.rel[k].val[e];
+                    fwd.col[dst] = k * n_j + rel[k].col[e];
+                    fwd.val[dst] = rel[k].val[e];
                 }
     }
     // backward: the transpose, K * n_j rows, column = u
     HostCsr bwd;
     csr_transpose(fwd, bwd);
 
-    G.staged = g->allow_staged && staged_supported(n_i, n_j, K) && G.F_j == n_j;
+    G.staged = g->allow_staged && staged_supported(n_i, n_j, G.K) && G.F_j == n_j;  // by the group-wide K: every rank agrees
     const long long target_warps = (long long)g->n_sm * 64 * 2;
     // one quarter-warp per segment: aim at ~2 waves of quarter-warps, 32..2048 non-zeros each
     int seg_len = (int)std::min<long long>(2048, std::max<long long>(32, (G.nnz / (4 * target_warps) + 31) / 32 * 32));
@@ -521,17 +555,17 @@ void build_group(dgn_graph *g, Group &G) {
     if (!G.bwd_seg.trivial) G.bwd_partial = dev_alloc<float>(panel_floats(P1, G.bwd_seg.n_seg));
 
     G.staged_version = g->staged_version;
-    if (G.staged && G.staged_version == 3 && !staged3_supported(n_i, n_j, K)) G.staged_version = 2;
-    G.tstaged = G.staged && g->allow_tstaged && tstaged_supported(n_i, n_j, K, P1);
+    if (G.staged && G.staged_version == 3 && !staged3_supported(n_i, n_j, G.K)) G.staged_version = 2;
+    G.tstaged = G.staged && g->allow_tstaged && tstaged_supported(n_i, n_j, G.K, P1);
     std::vector<long long> w_fwd(K), w_bwd(K);
-    for (int k = 0; k < K; ++k) w_fwd[k] = w_bwd[k] = G.rel[k].nnz() + G.rel[k].n_cols;
+    for (int k = 0; k < K; ++k) w_fwd[k] = w_bwd[k] = rel[k].nnz() + rel[k].n_cols;
     if (G.staged && G.staged_version == 3) {
-        G.task_fwd = plan_task_csr(G.rel, n_i, kS3Warps, false, true);
+        G.task_fwd = plan_task_csr(rel, n_i, kS3Warps, false, true);
         for (int k = 0; k < K; ++k) w_fwd[k] = G.task_fwd.rel_steps[k] + 64;
         // layer 1 runs P1 panel CTAs per slot, layer 2 one: the layer-2 slots are pieces of the layer-1 slots
         G.slots1 = build_slots(w_fwd, std::max(1, g->n_sm / P1));
         G.slots2 = split_slots(G.slots1, P1, w_fwd);
-        layout_task_csr(G.task_fwd, G.rel, G.slots1);
+        layout_task_csr(G.task_fwd, rel, G.slots1);
         G.wstart1 = upload_wstart(G.task_fwd, G.slots1);
         G.wstart2 = upload_wstart(G.task_fwd, G.slots2);
     } else if (G.staged) {
@@ -540,7 +574,7 @@ void build_group(dgn_graph *g, Group &G) {
     }
     if (G.tstaged) {
         std::vector<HostCsr> relt(K);
-        for (int k = 0; k < K; ++k) csr_transpose(G.rel[k], relt[k]);
+        for (int k = 0; k < K; ++k) csr_transpose(rel[k], relt[k]);
         G.task_bwd = plan_task_csr(relt, n_j, kTsWarps, true, false);
         for (int k = 0; k < K; ++k) w_bwd[k] = G.task_bwd.rel_steps[k] + 16;
         G.slots_bwd = build_slots(w_bwd, g->n_sm);
@@ -580,6 +614,63 @@ uint32_t dropout_threshold(float rate) {
     return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
 }
 
+const size_t kCommFlagBytes = (size_t)kMaxWorld * kMaxExchanges * sizeof(uint32_t);
+
+void free_comm(dgn_graph *g) {
+    for (int r = 0; r < kMaxWorld; ++r) {
+        if (g->peer_comm[r] && r != g->rank) cudaIpcCloseMemHandle(g->peer_comm[r]);
+        g->peer_comm[r] = nullptr;
+    }
+    if (g->peer_flags_dev) cudaFree(g->peer_flags_dev);
+    g->peer_flags_dev = nullptr;
+    if (g->comm) cudaFree(g->comm);
+    g->comm = nullptr;
+    g->comm_bytes = 0;
+    g->connected = false;
+}
+
+// exchange buffers of the partitioned groups (called from finalize)
+void build_comm(dgn_graph *g) {
+    free_comm(g);
+    if (g->world == 1) return;
+    size_t off = kCommFlagBytes;
+    int id = 0;
+    for (auto &G : g->groups) {
+        if (!G.partitioned) continue;
+        const size_t fl[3] = {panel_floats(g->P1, G.n_i), panel_floats(1, G.n_i), panel_floats(g->P1, G.n_j)};
+        for (int x = 0; x < 3; ++x) {
+            DGN_REQUIRE(id < kMaxExchanges, "too many partitioned groups");
+            G.xch[x].id = id++;
+            G.xch[x].floats = fl[x];
+            G.xch[x].off = off;
+            G.xch[x].stamp = 0;
+            off += 2 * fl[x] * sizeof(float);
+        }
+    }
+    g->n_exchanges = id;
+    g->comm_bytes = off;
+    CUDA_CHECK(cudaMalloc(&g->comm, off));
+    CUDA_CHECK(cudaMemset(g->comm, 0, off));
+    g->peer_comm[g->rank] = g->comm;
+}
+
+// Sum the local partials (fixed order) into this rank's buffer of exchange x, publish it and wait for
+// every peer; afterwards peer_ptr(r) of every rank may be read.  Collective: every rank calls it in the
+// same order.
+void exchange(dgn_graph *g, Group &G, int x, const float *partial, int n_chunks, cudaStream_t s) {
+    DGN_REQUIRE(g->connected, "dgn_comm_connect was not called");
+    Group::Exchange &X = G.xch[x];
+    ++X.stamp;
+    float *mine = reinterpret_cast<float *>(g->comm + X.off) + (X.stamp & 1) * X.floats;
+    launch_publish(partial, n_chunks, X.floats, mine, s);
+    launch_signal_wait(g->peer_flags_dev, reinterpret_cast<uint32_t *>(g->comm), g->rank, g->world, X.id, X.stamp, s);
+    g->launches += 2;
+}
+const float *peer_ptr(dgn_graph *g, const Group &G, int x, int r) {
+    const Group::Exchange &X = G.xch[x];
+    return reinterpret_cast<const float *>(g->peer_comm[r] + X.off) + (X.stamp & 1) * X.floats;
+}
+
 // Per-step dependency state: one Dep per tensor that crosses lanes.
 struct StepDeps {
     std::vector<Dep> S1, S2, dH;   // per group: layer-1 / layer-2 partial sums, dH partials
@@ -600,8 +691,8 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step, StepDep
         for (auto &G : g->groups) {
             PhaseScope ph(g, "mask", -1, G.lane);
             cudaStream_t s = lane_stream(g, G.lane);
-            launch_gen_mask(G.mask1, G.mask1_words, G.F_j, 0, G.r0, kStreamDropout1, step, seed, thr, s);
-            launch_gen_mask(G.mask2, G.mask2_words, (long long)G.n_j * g->d1, G.n_j * P1, G.r0, kStreamDropout2, step, seed, thr, s);
+            launch_gen_mask(G.mask1, G.mask1_words, G.F_j, 0, G.rel_ids, kStreamDropout1, step, seed, thr, s);
+            launch_gen_mask(G.mask2, G.mask2_words, (long long)G.n_j * g->d1, G.n_j * P1, G.rel_ids, kStreamDropout2, step, seed, thr, s);
             g->launches += 2;
         }
     }
@@ -612,7 +703,7 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step, StepDep
             TaskArgs a = {};
             a.hdr = G.task_fwd.hdr, a.ent = G.task_fwd.ent, a.orow = G.task_fwd.orow, a.orow_stride = 0;
             a.wstart = wstart;
-            a.K = G.K, a.n_warps = G.task_fwd.n_warps, a.rpq = G.task_fwd.rpq;
+            a.K = G.Kl, a.n_warps = G.task_fwd.n_warps, a.rpq = G.task_fwd.rpq;
             a.n_out_rows = G.n_i, a.n_op_rows = G.n_j;
             a.op = op, a.P = P;
             a.slot_ptr = slots.ptr, a.slot_rel = slots.rel, a.n_slots = slots.n_slots;
@@ -621,7 +712,7 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step, StepDep
         } else if (G.staged) {
             StagedArgs a = {};
             a.rowptr = G.relcsr.rowptr, a.col = G.relcsr.col, a.val = G.relcsr.val;
-            a.K = G.K, a.n_i = G.n_i, a.n_j = G.n_j;
+            a.K = G.Kl, a.n_i = G.n_i, a.n_j = G.n_j;
             a.op = op, a.P = P;
             a.slot_ptr = slots.ptr, a.slot_rel = slots.rel, a.n_slots = slots.n_slots;
             a.partial = part, a.mask = mask, a.scale = scale;
@@ -652,6 +743,10 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step, StepDep
             eg.partial = layer == 1 ? G.part1 : G.part2;
             eg.row_seg_ptr = G.staged ? nullptr : G.fwd_seg.row_seg_ptr;
             eg.n_slots = layer == 1 ? G.slots1.n_slots : G.slots2.n_slots;
+            if (G.partitioned) {
+                eg.n_peers = g->world;
+                for (int r = 0; r < g->world; ++r) eg.peer[r] = peer_ptr(g, G, layer - 1, r);
+            }
             eg.Y = layer == 1 ? G.Y1 : G.Y2;
             eg.nrm = layer == 1 ? G.n1 : G.n2;
         }
@@ -669,7 +764,8 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step, StepDep
         Group &G = g->groups[gi];
         {
             PhaseScope ph(g, "spmm_fwd1", gi, G.lane);
-            spmm_fwd(G, g->params + G.w1_off, P1, (long long)G.K * G.F_j, G.part1, G.slots1, G.wstart1, drop ? G.mask1 : nullptr);
+            spmm_fwd(G, g->params + G.w1_off, P1, (long long)G.Kl * G.F_j, G.part1, G.slots1, G.wstart1, drop ? G.mask1 : nullptr);
+            if (G.partitioned) exchange(g, G, 0, G.part1, G.slots1.n_slots, lane_stream(g, G.lane));
         }
         produced(g, D.S1[gi], G.lane);
     }
@@ -683,14 +779,15 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step, StepDep
             PhaseScope ph(g, "project", gi, G.lane);
             DenseArgs a = {};
             a.H = g->types[G.j].H, a.W2 = g->params + G.w2_off, a.P2 = G.P2;
-            a.mask = drop ? G.mask2 : nullptr, a.scale = scale, a.K = G.K, a.n_j = G.n_j;
+            a.mask = drop ? G.mask2 : nullptr, a.scale = scale, a.K = G.Kl, a.n_j = G.n_j;
             a.n_rb = G.n_rb, a.n_slots = G.slots_proj;
             launch_project(a, g->d1, g->d2, lane_stream(g, G.lane));
             g->launches++;
         }
         {
             PhaseScope ph(g, "spmm_fwd2", gi, G.lane);
-            spmm_fwd(G, G.P2, 1, (long long)G.K * G.n_j, G.part2, G.slots2, G.wstart2, nullptr);
+            spmm_fwd(G, G.P2, 1, (long long)G.Kl * G.n_j, G.part2, G.slots2, G.wstart2, nullptr);
+            if (G.partitioned) exchange(g, G, 1, G.part2, G.slots2.n_slots, lane_stream(g, G.lane));
         }
         produced(g, D.S2[gi], G.lane);
     }
@@ -713,7 +810,7 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam) {
             TaskArgs a = {};
             a.hdr = G.task_bwd.hdr, a.ent = G.task_bwd.ent, a.orow = G.task_bwd.orow, a.orow_stride = G.task_bwd.orow_stride;
             a.wstart = G.wstart_bwd;
-            a.K = G.K, a.n_warps = G.task_bwd.n_warps, a.rpq = G.task_bwd.rpq;
+            a.K = G.Kl, a.n_warps = G.task_bwd.n_warps, a.rpq = G.task_bwd.rpq;
             a.n_out_rows = G.n_j, a.n_op_rows = G.n_i;
             a.op = G.dS, a.P = P;
             a.slot_ptr = G.slots_bwd.ptr, a.slot_rel = G.slots_bwd.rel, a.n_slots = G.slots_bwd.n_slots;
@@ -759,11 +856,11 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam) {
         }
         {
             PhaseScope ph(g, "spmm_bwd2", gi, G.lane);
-            spmm_bwd(G, 1, G.G2, (long long)G.K * G.n_j, nullptr, false);
+            spmm_bwd(G, 1, G.G2, (long long)G.Kl * G.n_j, nullptr, false);
         }
         DenseArgs a = {};
         a.H = g->types[G.j].H, a.W2 = g->params + G.w2_off, a.G2 = G.G2;
-        a.mask = drop ? G.mask2 : nullptr, a.scale = scale, a.K = G.K, a.n_j = G.n_j;
+        a.mask = drop ? G.mask2 : nullptr, a.scale = scale, a.K = G.Kl, a.n_j = G.n_j;
         a.n_rb = G.n_rb;
         a.dW2 = G.n_rb > 1 ? G.dW2part : g->grads + G.w2_off;
         a.dHpart = G.dHpart;
@@ -773,7 +870,7 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam) {
             launch_dw2(a, g->d1, g->d2, s);
             g->launches++;
             if (G.n_rb > 1) {
-                launch_dw2_reduce(G.dW2part, g->grads + G.w2_off, G.K, G.n_rb, g->d1 * g->d2, s);
+                launch_dw2_reduce(G.dW2part, g->grads + G.w2_off, G.Kl, G.n_rb, g->d1 * g->d2, s);
                 g->launches++;
             }
         }
@@ -782,6 +879,7 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam) {
             a.n_slots = G.slots_dh;
             launch_dh(a, g->d1, g->d2, s);
             g->launches++;
+            if (G.partitioned) exchange(g, G, 2, G.dHpart, G.slots_dh, s);
         }
         produced(g, D.dH[gi], G.lane);
     }
@@ -797,6 +895,10 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam) {
                 consume(g, D.dH[gi], T.lane);
                 r.g[r.n_groups].part = g->groups[gi].dHpart;
                 r.g[r.n_groups].n_chunks = g->groups[gi].slots_dh;
+                if (g->groups[gi].partitioned) {
+                    r.g[r.n_groups].n_peers = g->world;
+                    for (int q = 0; q < g->world; ++q) r.g[r.n_groups].peer[q] = peer_ptr(g, g->groups[gi], 2, q);
+                }
                 r.n_groups++;
             }
             PhaseScope ph(g, "epilogue", -1, T.lane);
@@ -816,7 +918,7 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam) {
             g->launches++;
         }
         PhaseScope ph(g, "spmm_bwd1", gi, G.lane);
-        spmm_bwd(G, P1, g->grads + G.w1_off, (long long)G.K * G.F_j, drop ? G.mask1 : nullptr, adam.alpha != 0.f && G.tstaged && g->fuse_adam);
+        spmm_bwd(G, P1, g->grads + G.w1_off, (long long)G.Kl * G.F_j, drop ? G.mask1 : nullptr, adam.alpha != 0.f && G.tstaged && g->fuse_adam);
     }
     join_lanes(g, false);
 }
@@ -840,17 +942,18 @@ struct ParamSpan {
     long long row0, rows, stacked_rows;
 };
 
+// k is the LOCAL index for the encoder weights (W1 / W2) and the group-wide index for decoder variables
 ParamSpan locate_param(dgn_graph *g, int kind, int group, int k) {
-    DGN_REQUIRE(group >= 0 && group < g->n_groups, "group %d out of range", group);
     Group &G = g->groups[group];
-    DGN_REQUIRE(k >= -1 && k < G.K, "relation index %d out of range for group %d (K = %d)", k, group, G.K);
     ParamSpan s = {};
-    const long long nk = k < 0 ? G.K : 1, k0 = k < 0 ? 0 : k;
+    const bool encoder = kind == DGN_PARAM_W1 || kind == DGN_PARAM_W2;
+    const long long Kk = encoder ? G.Kl : G.K;
+    const long long nk = k < 0 ? Kk : 1, k0 = k < 0 ? 0 : k;
     switch (kind) {
         case DGN_PARAM_W1:
             s.panels = true;
             s.off = G.w1_off;
-            s.row0 = k0 * G.F_j, s.rows = nk * G.F_j, s.stacked_rows = (long long)G.K * G.F_j;
+            s.row0 = k0 * G.F_j, s.rows = nk * G.F_j, s.stacked_rows = (long long)G.Kl * G.F_j;
             s.count = s.rows * g->d1;
             break;
         case DGN_PARAM_W2:
@@ -870,6 +973,19 @@ ParamSpan locate_param(dgn_graph *g, int kind, int group, int k) {
         default: DGN_FAIL(DGN_ERR_INVALID, "unknown parameter kind %d", kind);
     }
     return s;
+}
+
+// floats of one relation's variable of this kind as they cross the C ABI
+long long param_floats_per_relation(dgn_graph *g, int kind, int group) {
+    Group &G = g->groups[group];
+    switch (kind) {
+        case DGN_PARAM_W1: return (long long)G.F_j * g->d1;
+        case DGN_PARAM_W2: return (long long)g->d1 * g->d2;
+        case DGN_PARAM_DEC_GLOBAL: return (long long)g->d2 * g->d2;
+        case DGN_PARAM_DEC_LOCAL: return (long long)G.loc_per_rel;
+        default: DGN_FAIL(DGN_ERR_INVALID, "unknown parameter kind %d", kind);
+    }
+    return 0;
 }
 
 void arena_write(dgn_graph *g, float *arena, const ParamSpan &s, const float *values) {
@@ -935,7 +1051,83 @@ PredictArgs predict_args(dgn_graph *g, int r, int count) {
     return a;
 }
 
+void free_arena(dgn_graph *g) {
+    dev_free(g->params);
+    dev_free(g->grads);
+    dev_free(g->adam_m);
+    dev_free(g->adam_v);
+    g->arena_ready = false;
+}
+
+// parameter arena: [W1 of every group | W2 of every group | decoder variables], encoder parts sized by
+// the LOCAL relation count of each group
+void layout_arena(dgn_graph *g) {
+    size_t off = 0;
+    for (auto &G : g->groups) {
+        G.w1_off = off;
+        off += (size_t)G.Kl * G.F_j * g->d1;
+    }
+    for (auto &G : g->groups) {
+        G.w2_off = off;
+        off += (size_t)G.Kl * g->d1 * g->d2;
+    }
+    g->dec_off = off;
+    for (auto &G : g->groups) {
+        if (G.decoder == DGN_DEC_DEDICOM) {
+            G.glb_off = off;
+            off += (size_t)g->d2 * g->d2;
+        }
+        G.loc_per_rel = G.decoder == DGN_DEC_BILINEAR ? (size_t)g->d2 * g->d2 : G.decoder == DGN_DEC_INNERPRODUCT ? 0 : (size_t)g->d2;
+        G.loc_off = off;
+        off += (size_t)G.K * G.loc_per_rel;
+    }
+    if (g->arena_ready && off == g->n_params) return;
+    free_arena(g);
+    g->n_params = off;
+    g->params = dev_alloc<float>(off);
+    g->grads = dev_alloc<float>(off);
+    g->adam_m = dev_alloc<float>(off);
+    g->adam_v = dev_alloc<float>(off);
+    CUDA_CHECK(cudaMemset(g->params, 0, off * sizeof(float)));
+    CUDA_CHECK(cudaMemset(g->grads, 0, off * sizeof(float)));
+    CUDA_CHECK(cudaMemset(g->adam_m, 0, off * sizeof(float)));
+    CUDA_CHECK(cudaMemset(g->adam_v, 0, off * sizeof(float)));
+    g->arena_ready = true;
+}
+
+void set_local_relations(Group &G, const std::vector<int> &loc) {
+    G.loc = loc;
+    G.Kl = (int)loc.size();
+    G.loc_index.assign(G.K, -1);
+    for (int l = 0; l < G.Kl; ++l) G.loc_index[loc[l]] = l;
+}
+
+void check_arena(dgn_graph *g) {
+    DGN_REQUIRE(g->arena_ready, "with more than one rank the parameters exist after dgn_graph_finalize (the partition needs the relations)");
+}
+
 }  // namespace
+
+extern "C" int dgn_partition_relations(const int64_t *weights, int32_t K, int32_t world, int32_t *owner_out) {
+    // longest-processing-time assignment, ties by index: every rank computes the same owners
+    if (!weights || !owner_out || K < 0 || world < 1) {
+        set_error("dgn_partition_relations: bad argument");
+        return DGN_ERR_INVALID;
+    }
+    std::vector<int> order(K);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return weights[x] > weights[y]; });
+    typedef std::pair<long long, int> Load;
+    std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+    for (int p = 0; p < world; ++p) heap.push(Load(0, p));
+    for (int k : order) {
+        Load l = heap.top();
+        heap.pop();
+        owner_out[k] = l.second;
+        heap.push(Load(l.first + weights[k], l.second));
+    }
+    return DGN_OK;
+}
 
 #define DGN_API_BEGIN try {
 #define DGN_API_END                         \
@@ -988,7 +1180,6 @@ extern "C" int dgn_graph_create(dgn_graph **out, int device, int n_types, const 
         g->types[t].F = feat_dim[t];
     }
     g->groups.resize(n_groups);
-    size_t off = 0;
     int r = 0;
     for (int gi = 0; gi < n_groups; ++gi) {
         Group &G = g->groups[gi];
@@ -1006,33 +1197,12 @@ extern "C" int dgn_graph_create(dgn_graph **out, int device, int n_types, const 
         r += G.K;
         g->types[G.i].row_groups.push_back(gi);
         g->types[G.j].col_groups.push_back(gi);
-        G.w1_off = off;
-        off += (size_t)G.K * G.F_j * hidden1;
+        std::vector<int> all(G.K);
+        std::iota(all.begin(), all.end(), 0);
+        set_local_relations(G, all);
     }
     g->R = r;
-    for (auto &G : g->groups) {
-        G.w2_off = off;
-        off += (size_t)G.K * hidden1 * hidden2;
-    }
-    g->dec_off = off;
-    for (auto &G : g->groups) {
-        if (G.decoder == DGN_DEC_DEDICOM) {
-            G.glb_off = off;
-            off += (size_t)hidden2 * hidden2;
-        }
-        G.loc_per_rel = G.decoder == DGN_DEC_BILINEAR ? (size_t)hidden2 * hidden2 : G.decoder == DGN_DEC_INNERPRODUCT ? 0 : (size_t)hidden2;
-        G.loc_off = off;
-        off += (size_t)G.K * G.loc_per_rel;
-    }
-    g->n_params = off;
-    g->params = dev_alloc<float>(off);
-    g->grads = dev_alloc<float>(off);
-    g->adam_m = dev_alloc<float>(off);
-    g->adam_v = dev_alloc<float>(off);
-    CUDA_CHECK(cudaMemset(g->params, 0, off * sizeof(float)));
-    CUDA_CHECK(cudaMemset(g->grads, 0, off * sizeof(float)));
-    CUDA_CHECK(cudaMemset(g->adam_m, 0, off * sizeof(float)));
-    CUDA_CHECK(cudaMemset(g->adam_v, 0, off * sizeof(float)));
+    layout_arena(g.get());  // one rank: every relation is local (dgn_comm_init re-partitions at finalize)
     {
         int lo = 0, hi = 0;
         CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -1049,6 +1219,7 @@ extern "C" int dgn_graph_create(dgn_graph **out, int device, int n_types, const 
         T.dA = dev_alloc<float>(panel_floats(g->P1, T.n));
         T.Z = dev_alloc<float>(panel_floats(1, T.n));
         T.dZ = dev_alloc<float>(panel_floats(1, T.n));
+        T.dZq = dev_alloc<long long>(panel_floats(1, T.n));
         CUDA_CHECK(cudaMemset(T.dZ, 0, panel_floats(1, T.n) * sizeof(float)));
     }
     const char *env = getenv("DGN_DISABLE_STAGED");
@@ -1078,12 +1249,11 @@ extern "C" int dgn_graph_destroy(dgn_graph *g) {
         dev_free(T.H);
         dev_free(T.Z);
         dev_free(T.dZ);
+        dev_free(T.dZq);
         dev_free(T.dA);
     }
-    dev_free(g->params);
-    dev_free(g->grads);
-    dev_free(g->adam_m);
-    dev_free(g->adam_v);
+    free_arena(g);
+    free_comm(g);
     dev_free(g->batch_dev);
     dev_free(g->neg_dev);
     dev_free(g->neg_out);
@@ -1171,7 +1341,29 @@ extern "C" int dgn_graph_finalize(dgn_graph *g) {
         DGN_REQUIRE(G.F_j == G.n_j, "identity features need feat_dim == n_nodes for type %d", G.j);
     }
     CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    for (auto &G : g->groups) {
+        // multi-GPU: groups that take the staged path (many small relations) are partitioned by relation
+        G.partitioned = g->world > 1 && g->allow_staged && staged_supported(G.n_i, G.n_j, G.K) && G.F_j == G.n_j && G.K >= 8 * g->world;
+        std::vector<int> loc;
+        if (G.partitioned) {
+            std::vector<int64_t> w(G.K);
+            for (int k = 0; k < G.K; ++k) w[k] = G.rel[k].nnz() + G.rel[k].n_cols;
+            G.owner.assign(G.K, 0);
+            dgn_partition_relations(w.data(), G.K, g->world, G.owner.data());
+            for (int k = 0; k < G.K; ++k)
+                if (G.owner[k] == g->rank) loc.push_back(k);
+        } else {
+            loc.resize(G.K);
+            std::iota(loc.begin(), loc.end(), 0);
+        }
+        set_local_relations(G, loc);
+    }
+    layout_arena(g);
     for (auto &G : g->groups) build_group(g, G);
+    build_comm(g);
+    // no device allocation may happen while a peer waits for this rank inside an exchange: take the batch
+    // buffers now (a larger batch later re-allocates; keep the ranks in step around such a change)
+    if (g->world > 1) ensure_batch_capacity(g, 4096);
     // stream lanes: the groups of many small relations (persistent one-CTA-per-SM kernels) on lane 0, the
     // rest on lane 1 so that their short kernels fill the gaps; per-type kernels follow their row groups
     bool any_staged = false;
@@ -1210,34 +1402,117 @@ extern "C" int dgn_graph_get_csr(dgn_graph *g, int r, int32_t *rowptr_out, int32
     DGN_API_END
 }
 
-extern "C" int dgn_params_set(dgn_graph *g, int kind, int group, int k, const float *values, int64_t n) {
-    DGN_API_BEGIN
+namespace {
+// k: group-wide relation index or -1 (all K stacked).  Encoder weights of relations another rank owns are
+// skipped on write and read back as zeros (dgn_relation_owner tells who has them).
+void param_io(dgn_graph *g, float *arena, int kind, int group, int k, float *values, int64_t n, bool write) {
     DGN_REQUIRE(g && values, "null argument");
     CUDA_CHECK(cudaSetDevice(g->device));
-    ParamSpan s = locate_param(g, kind, group, k);
-    DGN_REQUIRE(n == s.count, "parameter kind %d group %d k %d: got %lld floats, expected %lld", kind, group, k, (long long)n, s.count);
+    check_arena(g);
+    DGN_REQUIRE(group >= 0 && group < g->n_groups, "group %d out of range", group);
+    Group &G = g->groups[group];
+    DGN_REQUIRE(k >= -1 && k < G.K, "relation index %d out of range for group %d (K = %d)", k, group, G.K);
+    const long long per = param_floats_per_relation(g, kind, group);
+    const bool encoder = kind == DGN_PARAM_W1 || kind == DGN_PARAM_W2;
+    const long long nk = kind == DGN_PARAM_DEC_GLOBAL ? 1 : (k < 0 ? G.K : 1);
+    DGN_REQUIRE(n == nk * per, "parameter kind %d group %d k %d: got %lld floats, expected %lld", kind, group, k, (long long)n, nk * per);
     CUDA_CHECK(cudaStreamSynchronize(g->stream));
-    arena_write(g, g->params, s, values);
+    if (!encoder || !G.partitioned) {
+        ParamSpan s = locate_param(g, kind, group, k);
+        if (write) arena_write(g, arena, s, values);
+        else arena_read(g, arena, s, values);
+        return;
+    }
+    const int k0 = k < 0 ? 0 : k;
+    for (int kk = k0; kk < k0 + nk; ++kk) {
+        float *v = values + (size_t)(kk - k0) * per;
+        const int l = G.loc_index[kk];
+        if (l < 0) {
+            if (!write) memset(v, 0, (size_t)per * sizeof(float));
+            continue;
+        }
+        ParamSpan s = locate_param(g, kind, group, l);
+        if (write) arena_write(g, arena, s, v);
+        else arena_read(g, arena, s, v);
+    }
+}
+}  // namespace
+
+extern "C" int dgn_params_set(dgn_graph *g, int kind, int group, int k, const float *values, int64_t n) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(g, "null graph");
+    param_io(g, g->params, kind, group, k, const_cast<float *>(values), n, true);
     DGN_API_END
 }
 
 extern "C" int dgn_params_get(dgn_graph *g, int kind, int group, int k, float *values_out, int64_t n) {
     DGN_API_BEGIN
-    DGN_REQUIRE(g && values_out, "null argument");
-    CUDA_CHECK(cudaSetDevice(g->device));
-    ParamSpan s = locate_param(g, kind, group, k);
-    DGN_REQUIRE(n == s.count, "parameter kind %d group %d k %d: got %lld floats, expected %lld", kind, group, k, (long long)n, s.count);
-    arena_read(g, g->params, s, values_out);
+    DGN_REQUIRE(g, "null graph");
+    param_io(g, g->params, kind, group, k, values_out, n, false);
     DGN_API_END
 }
 
 extern "C" int dgn_grads_get(dgn_graph *g, int kind, int group, int k, float *values_out, int64_t n) {
     DGN_API_BEGIN
-    DGN_REQUIRE(g && values_out, "null argument");
+    DGN_REQUIRE(g, "null graph");
+    param_io(g, g->grads, kind, group, k, values_out, n, false);
+    DGN_API_END
+}
+
+extern "C" int dgn_relation_owner(dgn_graph *g, int r, int *owner_out) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(g && owner_out, "null argument");
+    DGN_REQUIRE(r >= 0 && r < g->R, "relation %d out of range", r);
+    Group &G = g->groups[g->flat[r].first];
+    DGN_REQUIRE(g->world == 1 || g->finalized, "the partition exists after dgn_graph_finalize");
+    *owner_out = !G.partitioned ? -1 : G.owner[g->flat[r].second];
+    DGN_API_END
+}
+
+extern "C" int dgn_comm_handle(dgn_graph *g, void *handle_out) {
+    DGN_API_BEGIN
+    check_finalized(g);
+    DGN_REQUIRE(handle_out && g->comm, "no exchange arena (one rank, or no partitioned group)");
     CUDA_CHECK(cudaSetDevice(g->device));
-    ParamSpan s = locate_param(g, kind, group, k);
-    DGN_REQUIRE(n == s.count, "gradient kind %d group %d k %d: got %lld floats, expected %lld", kind, group, k, (long long)n, s.count);
-    arena_read(g, g->grads, s, values_out);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the C ABI passes IPC handles as 64 bytes");
+    cudaIpcMemHandle_t h;
+    CUDA_CHECK(cudaIpcGetMemHandle(&h, g->comm));
+    memcpy(handle_out, &h, sizeof(h));
+    DGN_API_END
+}
+
+extern "C" int dgn_comm_connect(dgn_graph *g, const void *handles) {
+    DGN_API_BEGIN
+    check_finalized(g);
+    DGN_REQUIRE(handles && g->comm, "no exchange arena (one rank, or no partitioned group)");
+    CUDA_CHECK(cudaSetDevice(g->device));
+    std::vector<uint32_t *> flags(g->world);
+    for (int r = 0; r < g->world; ++r) {
+        if (r != g->rank) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, static_cast<const unsigned char *>(handles) + (size_t)r * sizeof(h), sizeof(h));
+            void *p = nullptr;
+            CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            g->peer_comm[r] = static_cast<unsigned char *>(p);
+        }
+        flags[r] = reinterpret_cast<uint32_t *>(g->peer_comm[r]);
+    }
+    if (g->peer_flags_dev) cudaFree(g->peer_flags_dev);
+    CUDA_CHECK(cudaMalloc(&g->peer_flags_dev, flags.size() * sizeof(uint32_t *)));
+    CUDA_CHECK(cudaMemcpy(g->peer_flags_dev, flags.data(), flags.size() * sizeof(uint32_t *), cudaMemcpyHostToDevice));
+    g->connected = true;
+    DGN_API_END
+}
+
+extern "C" int dgn_comm_init(dgn_graph *g, int rank, int world) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(g, "null graph");
+    DGN_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "rank %d of %d (at most %d ranks)", rank, world, kMaxWorld);
+    CUDA_CHECK(cudaSetDevice(g->device));
+    CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    g->rank = rank, g->world = world;
+    g->finalized = false;
+    if (world > 1) free_arena(g);  // the layout depends on the partition, which needs the relations: see finalize
     DGN_API_END
 }
 
@@ -1253,6 +1528,7 @@ extern "C" int dgn_optimizer_reset(dgn_graph *g, float beta1, float beta2, float
     DGN_REQUIRE(g, "null graph");
     CUDA_CHECK(cudaSetDevice(g->device));
     CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    check_arena(g);
     CUDA_CHECK(cudaMemset(g->adam_m, 0, g->n_params * sizeof(float)));
     CUDA_CHECK(cudaMemset(g->adam_v, 0, g->n_params * sizeof(float)));
     g->beta1 = beta1, g->beta2 = beta2, g->eps = epsilon;
@@ -1309,11 +1585,11 @@ extern "C" int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t
     {
         for (int t = 0; t < g->n_types; ++t) consume(g, deps.Z[t], 0);
         PhaseScope ph(g, "decode");
-        for (auto &T : g->types) CUDA_CHECK(cudaMemsetAsync(T.dZ, 0, panel_floats(1, T.n) * sizeof(float), s));
+        for (auto &T : g->types) CUDA_CHECK(cudaMemsetAsync(T.dZq, 0, panel_floats(1, T.n) * sizeof(long long), s));
         if (g->n_params > g->dec_off)
             CUDA_CHECK(cudaMemsetAsync(g->grads + g->dec_off, 0, (g->n_params - g->dec_off) * sizeof(float), s));
         DecodeArgs a = {};
-        a.Zi = g->types[G.i].Z, a.Zj = g->types[G.j].Z, a.dZi = g->types[G.i].dZ, a.dZj = g->types[G.j].dZ;
+        a.Zi = g->types[G.i].Z, a.Zj = g->types[G.j].Z, a.dZi = g->types[G.i].dZq, a.dZj = g->types[G.j].dZq;
         a.n_i = G.n_i, a.n_j = G.n_j;
         a.batch = g->batch_dev, a.neg_in = negatives ? g->neg_dev : nullptr, a.neg_out = g->neg_out;
         a.thr = G.thr[k], a.n_thr = G.thr_n[k];
@@ -1326,6 +1602,10 @@ extern "C" int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t
         a.seed_lo = (uint32_t)(seed & 0xffffffffu), a.seed_hi = (uint32_t)(seed >> 32), a.step = step, a.relation = (uint32_t)r;
         launch_decode(a, s);
         g->launches++;
+        for (auto &T : g->types) {
+            launch_fixed_to_float(T.dZq, T.dZ, panel_floats(1, T.n), s);
+            g->launches++;
+        }
         g->last_B = batch_size;
         for (int t = 0; t < g->n_types; ++t) produced(g, deps.dZ[t], 0);
     }
@@ -1352,7 +1632,7 @@ extern "C" int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t
         for (auto &Gq : g->groups)
             if (Gq.tstaged && g->fuse_adam && adam.alpha != 0.f) {
                 flush(Gq.w1_off);
-                begin = Gq.w1_off + (size_t)Gq.K * Gq.F_j * g->d1;
+                begin = Gq.w1_off + (size_t)Gq.Kl * Gq.F_j * g->d1;
             }
         flush(g->n_params);
         g->b1p *= g->beta1;

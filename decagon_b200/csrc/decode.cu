@@ -12,6 +12,8 @@
 //   M = loc glb loc;  a = M z_v;  s+ = z_u . a;  s- = z_n . a
 //   dZ_i[u] += ds+ a;  dZ_i[n] += ds- a;  dZ_j[v] += M^T (ds+ z_u + ds- z_n)   (float atomics)
 //   dM += (ds+ z_u + ds- z_n) z_v^T   (register tile per warp, ordered reduction over warps)
+#include <algorithm>
+
 #include "dgn_internal.cuh"
 #include "philox.cuh"
 
@@ -36,6 +38,15 @@ __device__ __forceinline__ float relation_entry(int decoder, const float *glb, c
         case DGN_DEC_BILINEAR: return loc[p * D + q];
         default: return loc[p] * glb[p * D + q] * loc[q];  // dedicom
     }
+}
+
+constexpr float kFixedScale = 1099511627776.f;  // 2^40
+__device__ __forceinline__ void fixed_add(long long *dst, float x) {
+    atomicAdd(reinterpret_cast<unsigned long long *>(dst), (unsigned long long)__float2ll_rn(x * kFixedScale));
+}
+__global__ void fixed_to_float_kernel(const long long *__restrict__ q, float *__restrict__ out, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (float)((double)q[i] * (1.0 / 1099511627776.0));
 }
 
 __global__ void __launch_bounds__(kDecodeThreads, 1) decode_kernel(const DecodeArgs a) {
@@ -107,9 +118,11 @@ __global__ void __launch_bounds__(kDecodeThreads, 1) decode_kernel(const DecodeA
             cv = fmaf(Ms[p][lane], wp, cv);
             dMcol[p] = fmaf(wp, zv, dMcol[p]);
         }
-        if (dpos != 0.f) atomicAdd(a.dZi + (size_t)u * D + lane, dpos * av);
-        if (dneg != 0.f) atomicAdd(a.dZi + (size_t)ng * D + lane, dneg * av);
-        if (dpos != 0.f || dneg != 0.f) atomicAdd(a.dZj + (size_t)v * D + lane, cv);
+        // nodes repeat inside a batch: the scatter-add runs on 2^-40 fixed-point integers, whose sums do not
+        // depend on the order of the atomics (float atomics would make the replicas of a multi-GPU run drift)
+        if (dpos != 0.f) fixed_add(a.dZi + (size_t)u * D + lane, dpos * av);
+        if (dneg != 0.f) fixed_add(a.dZi + (size_t)ng * D + lane, dneg * av);
+        if (dpos != 0.f || dneg != 0.f) fixed_add(a.dZj + (size_t)v * D + lane, cv);
     }
 
     if (lane == 0) loss_w[warp] = loss;
@@ -234,6 +247,12 @@ __global__ void relation_matrices_kernel(int decoder, const float *glb, const fl
 
 void launch_decode(const DecodeArgs &a, cudaStream_t s) {
     decode_kernel<<<1, kDecodeThreads, 0, s>>>(a);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_fixed_to_float(const long long *q, float *out, size_t n, cudaStream_t s) {
+    if (n == 0) return;
+    fixed_to_float_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(q, out, n);
     CUDA_CHECK(cudaGetLastError());
 }
 

@@ -68,6 +68,7 @@ struct SegTable {
 
 // ---------------------------------------------------------------- device-side argument blocks
 constexpr int kMaxGroupsPerType = 8;
+constexpr int kMaxWorld = 8;          // ranks of one NVSwitch box
 constexpr float kL2Eps = 1e-12f;  // tf.nn.l2_normalize epsilon (layers.py:93,117)
 
 struct SpmmArgs {
@@ -141,6 +142,8 @@ struct EpiGroup {
     const float *partial;
     const int *row_seg_ptr;  // segment mode; null => slot mode
     int n_slots;             // slot mode: partial[n_slots][P][n_rows][32]
+    int n_peers;             // > 0: peer mode, the sum over ranks (in rank order) of peer[r][P][n_rows][32]
+    const float *peer[kMaxWorld];
     float *Y;                // [P][n_rows][32] normalised rows
     float *nrm;              // [n_rows]  sqrt(max(|S|^2, eps))
 };
@@ -159,6 +162,8 @@ struct L2BwdArgs {  // dS = l2norm backward of one group
 struct ReluBwdGroup {
     const float *part;  // [n_chunks][P][n_rows][32]
     int n_chunks;
+    int n_peers;        // > 0: the sum over ranks (in rank order) of peer[r][P][n_rows][32] instead
+    const float *peer[kMaxWorld];
 };
 struct ReluBwdArgs {
     int n_rows, n_groups;
@@ -183,7 +188,7 @@ struct DenseArgs {
 
 struct DecodeArgs {
     const float *Zi, *Zj;  // [n][32]
-    float *dZi, *dZj;
+    long long *dZi, *dZj;  // 2^-40 fixed point (order-independent scatter-add)
     int n_i, n_j;
     const int *batch;   // [B][2]
     const long long *neg_in;  // [B] or null
@@ -223,7 +228,7 @@ bool staged_supported(int n_i, int n_j, int K);
 void launch_node_epilogue(const EpiArgs &a, int P, cudaStream_t s);
 void launch_l2norm_bwd(const L2BwdArgs &a, int P, cudaStream_t s);
 void launch_relu_bwd(const ReluBwdArgs &a, int P, cudaStream_t s);
-void launch_gen_mask(uint32_t *words, long long n_words, long long bits_per_rel, int words_per_rel_or_0, int r0,
+void launch_gen_mask(uint32_t *words, long long n_words, long long bits_per_rel, int words_per_rel_or_0, const int *rel_ids,
                      uint32_t stream_id, uint32_t step, uint64_t seed, uint32_t threshold, cudaStream_t s);
 int dense_row_block(int D1);
 void launch_project(const DenseArgs &a, int D1, int D2, cudaStream_t s);
@@ -231,11 +236,18 @@ void launch_dw2(const DenseArgs &a, int D1, int D2, cudaStream_t s);
 void launch_dw2_reduce(const float *part, float *out, int K, int n_chunks, int elems, cudaStream_t s);
 void launch_dh(const DenseArgs &a, int D1, int D2, cudaStream_t s);
 void launch_decode(const DecodeArgs &a, cudaStream_t s);
+void launch_fixed_to_float(const long long *q, float *out, size_t n, cudaStream_t s);
 void launch_predict(const PredictArgs &a, cudaStream_t s);
 void launch_predict_edges(const PredictArgs &a, const int *edges, int n_edges, int apply_sigmoid, float *out,
                           cudaStream_t s);
 void launch_adam(float *p, const float *g, float *m, float *v, long long n, float alpha, float one_minus_b1,
                  float one_minus_b2, float eps, cudaStream_t s);
+// multi-GPU exchange (node.cu): ordered sum of the local partials into this rank's exchange buffer; then
+// "exchange x reached stamp" is stored into every peer's flag array and awaited from every peer
+void launch_publish(const float *partial, int n_chunks, size_t floats, float *out, cudaStream_t s);
+void launch_signal_wait(uint32_t *const *peer_flags_dev, uint32_t *my_flags, int rank, int world, int x, uint32_t stamp,
+                        cudaStream_t s);
+constexpr int kMaxExchanges = 16;  // flag slots per source rank
 void launch_relation_matrices(int decoder, const float *glb, const float *loc, float *glb_out, float *loc_out,
                               cudaStream_t s);
 

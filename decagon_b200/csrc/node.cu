@@ -36,7 +36,11 @@ __global__ void __launch_bounds__(256) node_epilogue_kernel(const EpiArgs a) {
         float s[P];
 #pragma unroll
         for (int p = 0; p < P; ++p) s[p] = 0.f;
-        if (g.row_seg_ptr != nullptr) {
+        if (g.n_peers > 0) {
+            for (int r = 0; r < g.n_peers; ++r)
+#pragma unroll
+                for (int p = 0; p < P; ++p) s[p] += g.peer[r][((size_t)p * a.n_rows + row) * 32 + lane];
+        } else if (g.row_seg_ptr != nullptr) {
             const int s0 = g.row_seg_ptr[row], s1 = g.row_seg_ptr[row + 1];
             for (int sg = s0; sg < s1; ++sg)
 #pragma unroll
@@ -92,8 +96,12 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const ReluBwdArgs a) {
     const size_t n = (size_t)P * a.n_rows * 32;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float s = 0.f;
-        for (int gi = 0; gi < a.n_groups; ++gi)
-            for (int c = 0; c < a.g[gi].n_chunks; ++c) s += a.g[gi].part[(size_t)c * n + i];
+        for (int gi = 0; gi < a.n_groups; ++gi) {
+            if (a.g[gi].n_peers > 0)
+                for (int r = 0; r < a.g[gi].n_peers; ++r) s += a.g[gi].peer[r][i];
+            else
+                for (int c = 0; c < a.g[gi].n_chunks; ++c) s += a.g[gi].part[(size_t)c * n + i];
+        }
         a.dA[i] = a.H[i] > 0.f ? s : 0.f;
     }
 }
@@ -103,7 +111,7 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const ReluBwdArgs a) {
 // words_per_rel == 0: relations are packed back to back at bit granularity (layer 1, bit index
 // = rel * bits_per_rel + e); otherwise each relation owns words_per_rel whole words (layer 2).
 __global__ void gen_mask_kernel(uint32_t *__restrict__ words, long long n_words, long long bits_per_rel,
-                                int words_per_rel, int r0, uint32_t stream_id, uint32_t step, uint32_t seed_lo,
+                                int words_per_rel, const int *__restrict__ rel_ids, uint32_t stream_id, uint32_t step, uint32_t seed_lo,
                                 uint32_t seed_hi, uint32_t threshold, long long total_bits) {
     const long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (w >= n_words) return;
@@ -113,11 +121,12 @@ __global__ void gen_mask_kernel(uint32_t *__restrict__ words, long long n_words,
         // word-aligned relations: 8 Philox calls give the 32 bits of this word
         const long long rel = w / words_per_rel;
         const long long e0 = (w - rel * words_per_rel) * 32;
+        const uint32_t rid = (uint32_t)rel_ids[rel];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const long long e = e0 + 4 * q;
             if (e >= bits_per_rel) break;
-            const uint4 rnd = philox4x32_10(make_uint4((uint32_t)(e >> 2), (uint32_t)(r0 + rel), stream_id, step), key);
+            const uint4 rnd = philox4x32_10(make_uint4((uint32_t)(e >> 2), rid, stream_id, step), key);
             out |= (rnd.x >= threshold ? 1u : 0u) << (4 * q);
             if (e + 1 < bits_per_rel) out |= (rnd.y >= threshold ? 1u : 0u) << (4 * q + 1);
             if (e + 2 < bits_per_rel) out |= (rnd.z >= threshold ? 1u : 0u) << (4 * q + 2);
@@ -134,7 +143,7 @@ __global__ void gen_mask_kernel(uint32_t *__restrict__ words, long long n_words,
         const long long rel = bit / bits_per_rel, e = bit % bits_per_rel;
         const long long ctr = e >> 2;
         if (rel != cached_rel || ctr != cached_ctr) {
-            rnd = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(r0 + rel), stream_id, step), key);
+            rnd = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)rel_ids[rel], stream_id, step), key);
             cached_rel = rel;
             cached_ctr = ctr;
         }
@@ -174,6 +183,34 @@ __global__ void __launch_bounds__(256) adam_kernel(float *__restrict__ p, const 
     }
 }
 
+// ---- multi-GPU exchange -------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) publish_kernel(const float4 *__restrict__ partial, int n_chunks, size_t n4,
+                                                      float4 *__restrict__ out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < n_chunks; ++c) {
+            const float4 x = partial[(size_t)c * n4 + i];
+            s.x += x.x, s.y += x.y, s.z += x.z, s.w += x.w;
+        }
+        out[i] = s;
+    }
+}
+
+// One CTA, thread t talks to rank t.  The exchange buffer was written by the previous kernel of this
+// stream; peers read it through NVLink after they see the stamp.
+__global__ void signal_wait_kernel(uint32_t *const *__restrict__ peer_flags, uint32_t *my_flags, int rank, int world, int x,
+                                   uint32_t stamp) {
+    const int t = threadIdx.x;
+    if (t >= world) return;
+    __threadfence_system();
+    volatile uint32_t *dst = peer_flags[t] + rank * kMaxExchanges + x;
+    *dst = stamp;
+    volatile uint32_t *src = my_flags + t * kMaxExchanges + x;
+    for (long long spin = 0; (int)(*src - stamp) < 0; ++spin)
+        if (spin > (1ll << 28)) __trap();  // a lost peer must fault, not hang the GPU
+    __threadfence_system();
+}
+
 template <typename F>
 void dispatch_panels(int P, F &&f) {
     switch (P) {
@@ -208,12 +245,26 @@ void launch_relu_bwd(const ReluBwdArgs &a, int P, cudaStream_t s) {
     CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_gen_mask(uint32_t *words, long long n_words, long long bits_per_rel, int words_per_rel, int r0,
+void launch_publish(const float *partial, int n_chunks, size_t floats, float *out, cudaStream_t s) {
+    const size_t n4 = floats / 4;
+    if (n4 == 0) return;
+    dim3 grid((unsigned)std::min<size_t>((n4 + 255) / 256, 148 * 4)), block(256);
+    publish_kernel<<<grid, block, 0, s>>>(reinterpret_cast<const float4 *>(partial), n_chunks, n4, reinterpret_cast<float4 *>(out));
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_signal_wait(uint32_t *const *peer_flags_dev, uint32_t *my_flags, int rank, int world, int x, uint32_t stamp,
+                        cudaStream_t s) {
+    signal_wait_kernel<<<1, 32, 0, s>>>(peer_flags_dev, my_flags, rank, world, x, stamp);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_gen_mask(uint32_t *words, long long n_words, long long bits_per_rel, int words_per_rel, const int *rel_ids,
                      uint32_t stream_id, uint32_t step, uint64_t seed, uint32_t threshold, cudaStream_t s) {
     if (n_words == 0) return;
     const long long total_bits = n_words * 32;  // packed mode: caller rounds the word count up
     dim3 grid((unsigned)((n_words + 255) / 256)), block(256);
-    gen_mask_kernel<<<grid, block, 0, s>>>(words, n_words, bits_per_rel, words_per_rel, r0, stream_id, step,
+    gen_mask_kernel<<<grid, block, 0, s>>>(words, n_words, bits_per_rel, words_per_rel, rel_ids, stream_id, step,
                                            (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), threshold,
                                            total_bits);
     CUDA_CHECK(cudaGetLastError());

@@ -52,6 +52,37 @@ class Engine(object):
         except Exception:
             pass
 
+    # ------------------------------------------------------------------ one process per GPU
+    def comm_init(self, rank, world):
+        """Partition the many-relation groups over ``world`` ranks (call before ``load_iterator``)."""
+        check(self.lib.dgn_comm_init(self._h, int(rank), int(world)))
+        self.rank, self.world = int(rank), int(world)
+        self.finalized = False
+
+    def comm_handle(self):
+        """64-byte CUDA IPC handle of this rank's exchange arena (after ``finalize``)."""
+        buf = ctypes.create_string_buffer(64)
+        check(self.lib.dgn_comm_handle(self._h, ctypes.cast(buf, ctypes.c_void_p)))
+        return buf.raw
+
+    def comm_connect(self, handles):
+        """handles: the ``world`` 64-byte handles in rank order (an all-gather of ``comm_handle()``)."""
+        blob = b''.join(handles)
+        buf = ctypes.create_string_buffer(blob, len(blob))
+        check(self.lib.dgn_comm_connect(self._h, ctypes.cast(buf, ctypes.c_void_p)))
+
+    def connect(self, dist):
+        """Exchange the arena handles through an initialised ``torch.distributed`` (any backend)."""
+        handles = [None] * dist.get_world_size()
+        dist.all_gather_object(handles, self.comm_handle())
+        self.comm_connect(handles)
+        dist.barrier()
+
+    def relation_owner(self, r):
+        o = ctypes.c_int(0)
+        check(self.lib.dgn_relation_owner(self._h, int(r), ctypes.byref(o)))
+        return o.value
+
     # ------------------------------------------------------------------ graph
     def set_relation(self, r, coords, values, shape):
         """(coords int[nnz,2], values, shape) exactly as ``adj_train[i,j][k]``; values are cast to

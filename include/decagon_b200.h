@@ -107,6 +107,26 @@ int dgn_graph_finalize(dgn_graph *g);
 int dgn_graph_relation_nnz(dgn_graph *g, int r, int64_t *nnz_out);
 int dgn_graph_get_csr(dgn_graph *g, int r, int32_t *rowptr_out, int32_t *col_out, float *val_out);
 
+/* ---- one process per GPU (the reference is single-device) ----------------------
+ * The relations of every group that takes the staged path (many small relations: the 964 drug-drug side
+ * effects and their transposes) are partitioned over `world` ranks of ONE NVSwitch box: a rank keeps the
+ * adjacency, layer-1 / layer-2 weights, dropout words and Adam state of its own relations only.  The other
+ * groups and every decoder variable are replicated.  Per step three partial sums ([n_i, hidden1],
+ * [n_i, hidden2], [n_j, hidden1] per partitioned group) are exchanged: every rank publishes its partial in
+ * its exchange arena and reads the peers' arenas over NVLink (CUDA IPC mappings), summing in rank order, so
+ * all ranks hold bit-identical embeddings.  Call order: dgn_graph_create, dgn_comm_init, dgn_graph_set_* for
+ * ALL relations on every rank, dgn_graph_finalize, dgn_comm_handle -> all-gather of the 64-byte handles by
+ * the host program -> dgn_comm_connect, then parameters and compute.  dgn_encoder_forward and dgn_train_step
+ * are collective.  With world > 1 the parameter arena exists after dgn_graph_finalize. */
+int dgn_comm_init(dgn_graph *g, int rank, int world);
+int dgn_comm_handle(dgn_graph *g, void *handle_out_64_bytes);
+int dgn_comm_connect(dgn_graph *g, const void *handles /* [world][64] */);
+/* owner rank of flat relation r (-1: its group is replicated); dgn_params_get / dgn_grads_get return
+ * zeros for the encoder weights of relations another rank owns, dgn_params_set skips them */
+int dgn_relation_owner(dgn_graph *g, int r, int *owner_out);
+/* host-only: the longest-processing-time assignment the library uses (weights = nnz + columns) */
+int dgn_partition_relations(const int64_t *weights, int32_t K, int32_t world, int32_t *owner_out);
+
 /* ---- parameters (tf.Variable) ------------------------------------------------------------ */
 
 /* k >= 0: one relation's variable; k == -1: all K variables of the group, stacked.
