@@ -5,7 +5,8 @@
 
 Every rank trains the mini polypharmacy-shape graph for a few steps with the relations of the drug-drug
 group partitioned over the ranks, rank 0 also runs the same steps on an un-partitioned engine; losses,
-embeddings and the parameters each rank owns must agree to 1e-5, and all ranks must hold bit-identical
+embeddings and the parameters each rank owns must agree (1e-5 on the same parameters, 1e-4 after six Adam
+steps), and all ranks must hold bit-identical
 embeddings.  (Needs GPUs: not collected by pytest; the host-side partition logic is covered on CPU by
 tests/test_partition.py.)"""
 import os
@@ -53,9 +54,11 @@ def main():
     # Rank 0 first runs the steps on an un-partitioned engine, alone.  (No device allocation may happen on a
     # GPU while a peer waits for it inside an exchange: a second engine is never built next to a live
     # partitioned one.)
-    ref_loss, ref_Z, ref_p = [], {}, None
+    ref_loss, ref_Z, ref_Z0, ref_p = [], {}, {}, None
     if rank == 0:
         ref = make(False)
+        ref.forward()
+        ref_Z0 = {t: ref.embeddings(t) for t in inputs.n_nodes}
         for step, (r, batch) in enumerate(batches):
             ref_loss.append(float(ref.train_step(r, batch, dropout=0.1, seed=11, step=step)))
         ref.forward()
@@ -66,6 +69,8 @@ def main():
     dist.barrier()
     part = make(True)
     say('partitioned engine connected')
+    part.forward()
+    Z0 = {t: part.embeddings(t) for t in inputs.n_nodes}
     losses = [float(part.train_step(r, batch, dropout=0.1, seed=11, step=step)) for step, (r, batch) in enumerate(batches)]
     say('steps done: %s' % losses[:2])
     part.forward()
@@ -77,6 +82,12 @@ def main():
         dist.all_gather_object(everyone, Z[t].tobytes())
         assert all(e == everyone[0] for e in everyone), 'embeddings of type %d differ between ranks' % t
     if rank == 0:
+        # same parameters: the partitioned forward and the first loss agree to the fp32 contract (1e-5)
+        first = max([rel_err(Z0[t], ref_Z0[t]) for t in Z0] + [abs(losses[0] - ref_loss[0]) / abs(ref_loss[0])])
+        print('multigpu_check: first forward / first loss rel-err %.2e' % first)
+        assert first <= 1e-5, first
+        # six Adam steps later: Adam's m / sqrt(v) amplifies re-association differences of tiny gradients, the
+        # trajectories agree to 1e-4
         worst = max(abs(a - b) / max(abs(b), 1e-30) for a, b in zip(losses, ref_loss))
         for t in Z:
             worst = max(worst, rel_err(Z[t], ref_Z[t]))
@@ -92,7 +103,7 @@ def main():
                 if a.size:
                     worst = max(worst, rel_err(a, b))
         print('multigpu_check: world %d, losses %s, worst rel-err vs one GPU %.2e' % (world, losses[:3], worst))
-        assert worst <= 1e-5, worst
+        assert worst <= 1e-4, worst
     dist.barrier()
     if rank == 0:
         print('multigpu_check OK')
