@@ -347,7 +347,7 @@ struct Group {
     float *P2 = nullptr, *dS = nullptr, *G2 = nullptr, *bwd_partial = nullptr, *dW2part = nullptr, *dHpart = nullptr;
     uint32_t *mask1 = nullptr, *mask2 = nullptr;
     long long mask1_words = 0, mask2_words = 0;
-    int n_rb = 1, slots_proj = 1, slots_dh = 1;  // dense layer-2 kernels: row blocks, persistent CTAs per block
+    int n_rb = 1, n_rb_pd = 1, slots_proj = 1, slots_dh = 1, slots_dw2 = 1;  // dense layer-2 kernels: row blocks, CTAs per block
     std::vector<uint32_t *> thr;  // per relation
     std::vector<int> thr_n;
 };
@@ -397,6 +397,8 @@ struct dgn_graph {
     int *batch_dev = nullptr;
     long long *neg_dev = nullptr, *neg_out = nullptr;
     float *pos_out = nullptr, *negs_out = nullptr, *loss_dev = nullptr, *loss_host = nullptr;
+    float *decode_scratch = nullptr;
+    unsigned *decode_ticket = nullptr;
     int last_B = 0;
     // measurement
     bool timing = false;
@@ -601,10 +603,12 @@ void build_group(dgn_graph *g, Group &G) {
     G.mask2 = dev_alloc<uint32_t>((size_t)G.mask2_words);
 
     // dense layer-2 kernels: persistent CTAs, one per (row block, slot of relations)
-    const int RB = dense_row_block(g->d1);
-    G.n_rb = (n_j + RB - 1) / RB;
-    G.slots_proj = std::max(1, std::min(K, g->n_sm / G.n_rb));
-    G.slots_dh = std::max(1, std::min(K, g->n_sm / (P1 * G.n_rb)));
+    const int RB = dense_row_block(g->d1, 1), RBpd = dense_row_block(g->d1, 0);
+    G.n_rb = (n_j + RB - 1) / RB;        // dw2
+    G.n_rb_pd = (n_j + RBpd - 1) / RBpd;  // project, dh
+    G.slots_dw2 = std::max(1, std::min(K, g->n_sm / G.n_rb));
+    G.slots_proj = std::max(1, std::min(K, g->n_sm / G.n_rb_pd));
+    G.slots_dh = std::max(1, std::min(K, g->n_sm / (P1 * G.n_rb_pd)));
     if (G.n_rb > 1) G.dW2part = dev_alloc<float>((size_t)K * G.n_rb * g->d1 * g->d2);
     G.dHpart = dev_alloc<float>((size_t)G.slots_dh * panel_floats(P1, n_j));
 }
@@ -780,7 +784,7 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step, StepDep
             DenseArgs a = {};
             a.H = g->types[G.j].H, a.W2 = g->params + G.w2_off, a.P2 = G.P2;
             a.mask = drop ? G.mask2 : nullptr, a.scale = scale, a.K = G.Kl, a.n_j = G.n_j;
-            a.n_rb = G.n_rb, a.n_slots = G.slots_proj;
+            a.n_rb = G.n_rb_pd, a.n_slots = G.slots_proj;
             launch_project(a, g->d1, g->d2, lane_stream(g, G.lane));
             g->launches++;
         }
@@ -866,7 +870,7 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam) {
         a.dHpart = G.dHpart;
         {
             PhaseScope ph(g, "dw2", gi, G.lane);
-            a.n_slots = G.slots_proj;
+            a.n_slots = G.slots_dw2;
             launch_dw2(a, g->d1, g->d2, s);
             g->launches++;
             if (G.n_rb > 1) {
@@ -876,7 +880,7 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam) {
         }
         {
             PhaseScope ph(g, "dh", gi, G.lane);
-            a.n_slots = G.slots_dh;
+            a.n_slots = G.slots_dh, a.n_rb = G.n_rb_pd;
             launch_dh(a, g->d1, g->d2, s);
             g->launches++;
             if (G.partitioned) exchange(g, G, 2, G.dHpart, G.slots_dh, s);
@@ -1212,6 +1216,9 @@ extern "C" int dgn_graph_create(dgn_graph **out, int device, int n_types, const 
     g->own_stream = true;
     for (int i = 0; i < dgn_graph::kRing; ++i) CUDA_CHECK(cudaEventCreateWithFlags(&g->ring_ev[i], cudaEventDisableTiming));
     g->loss_dev = dev_alloc<float>(1);
+    g->decode_scratch = dev_alloc<float>((size_t)kDecodeCtas * (32 * 32 + 1));
+    g->decode_ticket = dev_alloc<unsigned>(1);
+    CUDA_CHECK(cudaMemset(g->decode_ticket, 0, sizeof(unsigned)));
     CUDA_CHECK(cudaMallocHost(&g->loss_host, sizeof(float)));
     for (int t = 0; t < n_types; ++t) {
         NodeType &T = g->types[t];
@@ -1260,6 +1267,8 @@ extern "C" int dgn_graph_destroy(dgn_graph *g) {
     dev_free(g->pos_out);
     dev_free(g->negs_out);
     dev_free(g->loss_dev);
+    dev_free(g->decode_scratch);
+    dev_free(g->decode_ticket);
     if (g->loss_host) cudaFreeHost(g->loss_host);
     for (int i = 0; i < dgn_graph::kRing; ++i) {
         if (g->batch_host[i]) cudaFreeHost(g->batch_host[i]);
@@ -1600,6 +1609,7 @@ extern "C" int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t
         a.g_loc = G.loc_per_rel ? g->grads + G.loc_off + (size_t)k * G.loc_per_rel : nullptr;
         a.pos_out = g->pos_out, a.neg_score_out = g->negs_out, a.loss_out = g->loss_dev;
         a.seed_lo = (uint32_t)(seed & 0xffffffffu), a.seed_hi = (uint32_t)(seed >> 32), a.step = step, a.relation = (uint32_t)r;
+        a.scratch = g->decode_scratch, a.ticket = g->decode_ticket;
         launch_decode(a, s);
         g->launches++;
         for (auto &T : g->types) {

@@ -49,11 +49,16 @@ __global__ void fixed_to_float_kernel(const long long *__restrict__ q, float *__
         out[i] = (float)((double)q[i] * (1.0 / 1099511627776.0));
 }
 
+// Grid of kDecodeCtas CTAs, each takes a contiguous slice of the batch (one warp per edge); the last CTA to
+// finish (ticket counter) adds the CTAs' loss and dM partials in CTA order, so the sums have a fixed order.
 __global__ void __launch_bounds__(kDecodeThreads, 1) decode_kernel(const DecodeArgs a) {
     __shared__ float Ms[D][D + 1];
     __shared__ float dMs[D][D + 1];
     __shared__ float loss_w[kDecodeThreads / 32];
+    __shared__ int is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int per = (a.B + gridDim.x - 1) / gridDim.x;
+    const int b0 = blockIdx.x * per, b1 = min(b0 + per, a.B);
 
     for (int i = threadIdx.x; i < D * D; i += blockDim.x) {
         const int p = i >> 5, q = i & 31;
@@ -61,7 +66,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 1) decode_kernel(const DecodeA
         dMs[p][q] = 0.f;
     }
     // negatives: index = #{v : thr[v] <= u32}, clamped (optimizer.py:40-47 restated)
-    for (int b = threadIdx.x; b < a.B; b += blockDim.x) {
+    for (int b = b0 + threadIdx.x; b < b1; b += blockDim.x) {
         long long neg;
         if (a.neg_in != nullptr) {
             neg = a.neg_in[b];
@@ -85,7 +90,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 1) decode_kernel(const DecodeA
     for (int p = 0; p < D; ++p) dMcol[p] = 0.f;
     float loss = 0.f;
 
-    for (int b = warp; b < a.B; b += n_warps) {
+    for (int b = b0 + warp; b < b1; b += n_warps) {
         const int u = a.batch[2 * b], v = a.batch[2 * b + 1];
         const int ng = (int)a.neg_out[b];
         const float zu = a.Zi[(size_t)u * D + lane], zn = a.Zi[(size_t)ng * D + lane], zv = a.Zj[(size_t)v * D + lane];
@@ -133,11 +138,35 @@ __global__ void __launch_bounds__(kDecodeThreads, 1) decode_kernel(const DecodeA
         }
         __syncthreads();
     }
+    // this CTA's partials
+    float *part = a.scratch + (size_t)blockIdx.x * (D * D + 1);
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x) part[i] = dMs[i >> 5][i & 31];
     if (threadIdx.x == 0) {
         float s = 0.f;
         for (int w = 0; w < n_warps; ++w) s += loss_w[w];
+        part[D * D] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned ticket = atomicAdd(a.ticket, 1u);
+        is_last = ticket == gridDim.x - 1;
+        if (is_last) *a.ticket = 0u;  // ready for the next launch
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x) {
+        float s = 0.f;
+        for (unsigned c = 0; c < gridDim.x; ++c) s += a.scratch[(size_t)c * (D * D + 1) + i];
+        dMs[i >> 5][i & 31] = s;
+    }
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (unsigned c = 0; c < gridDim.x; ++c) s += a.scratch[(size_t)c * (D * D + 1) + D * D];
         *a.loss_out = s;
     }
+    __syncthreads();
     // decoder-parameter gradients
     for (int i = threadIdx.x; i < D * D; i += blockDim.x) {  // blockDim is a multiple of 32: q == lane
         const int p = i >> 5, q = i & 31;
@@ -246,7 +275,7 @@ __global__ void relation_matrices_kernel(int decoder, const float *glb, const fl
 }  // namespace
 
 void launch_decode(const DecodeArgs &a, cudaStream_t s) {
-    decode_kernel<<<1, kDecodeThreads, 0, s>>>(a);
+    decode_kernel<<<kDecodeCtas, kDecodeThreads, 0, s>>>(a);
     CUDA_CHECK(cudaGetLastError());
 }
 

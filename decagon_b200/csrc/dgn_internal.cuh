@@ -201,7 +201,10 @@ struct DecodeArgs {
     float *g_glb, *g_loc;     // their gradients
     float *pos_out, *neg_score_out, *loss_out;
     uint32_t seed_lo, seed_hi, step, relation;
+    float *scratch;      // [kDecodeCtas][32 * 32 + 1] per-CTA dM and loss partials
+    unsigned *ticket;    // zero between launches
 };
+constexpr int kDecodeCtas = 16;
 
 struct PredictArgs {
     const float *Zi, *Zj;
@@ -230,7 +233,7 @@ void launch_l2norm_bwd(const L2BwdArgs &a, int P, cudaStream_t s);
 void launch_relu_bwd(const ReluBwdArgs &a, int P, cudaStream_t s);
 void launch_gen_mask(uint32_t *words, long long n_words, long long bits_per_rel, int words_per_rel_or_0, const int *rel_ids,
                      uint32_t stream_id, uint32_t step, uint64_t seed, uint32_t threshold, cudaStream_t s);
-int dense_row_block(int D1);
+int dense_row_block(int D1, int which);
 void launch_project(const DenseArgs &a, int D1, int D2, cudaStream_t s);
 void launch_dw2(const DenseArgs &a, int D1, int D2, cudaStream_t s);
 void launch_dw2_reduce(const float *part, float *out, int K, int n_chunks, int elems, cudaStream_t s);

@@ -69,6 +69,74 @@ __global__ void __launch_bounds__(256) node_epilogue_kernel(const EpiArgs a) {
         a.out[((size_t)p * a.n_rows + row) * 32 + lane] = a.relu ? fmaxf(total[p], 0.f) : total[p];
 }
 
+// Same result layout for node types with few rows whose groups carry many slot partials (645 drugs x 74..148
+// slots): one CTA per row, the 8 warps sum contiguous chunks of the slots, the chunk sums are added in order.
+template <int P>
+__global__ void __launch_bounds__(256) node_epilogue_wide_kernel(const EpiArgs a) {
+    __shared__ float red[8][P][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = blockIdx.x;
+    float total[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) total[p] = 0.f;
+    for (int gi = 0; gi < a.n_groups; ++gi) {
+        const EpiGroup &g = a.g[gi];
+        float s[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) s[p] = 0.f;
+        if (g.n_peers > 0) {
+            for (int r = warp; r < g.n_peers; r += 8)
+#pragma unroll
+                for (int p = 0; p < P; ++p) s[p] += g.peer[r][((size_t)p * a.n_rows + row) * 32 + lane];
+        } else if (g.row_seg_ptr != nullptr) {
+            const int s0 = g.row_seg_ptr[row], s1 = g.row_seg_ptr[row + 1];
+            const int per = (s1 - s0 + 7) / 8;
+            for (int sg = s0 + warp * per; sg < min(s0 + (warp + 1) * per, s1); ++sg)
+#pragma unroll
+                for (int p = 0; p < P; ++p) s[p] += g.partial[((size_t)sg * P + p) * 32 + lane];
+        } else {
+            const int per = (g.n_slots + 7) / 8;
+            for (int sl = warp * per; sl < min((warp + 1) * per, g.n_slots); ++sl)
+#pragma unroll
+                for (int p = 0; p < P; ++p) s[p] += g.partial[(((size_t)sl * P + p) * a.n_rows + row) * 32 + lane];
+        }
+#pragma unroll
+        for (int p = 0; p < P; ++p) red[warp][p][lane] = s[p];
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                float t = 0.f;
+                if (g.n_peers > 0 && g.n_peers <= 8) {
+                    for (int r = 0; r < g.n_peers; ++r) t += red[r][p][lane];  // rank order: every rank gets the same bits
+                } else {
+                    for (int w = 0; w < 8; ++w) t += red[w][p][lane];
+                }
+                s[p] = t;
+            }
+            float sq = 0.f;
+#pragma unroll
+            for (int p = 0; p < P; ++p) sq = fmaf(s[p], s[p], sq);
+            sq = warp_sum(sq);
+            const float nrm = sqrtf(fmaxf(sq, kL2Eps));
+            const float inv = 1.f / nrm;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const float y = s[p] * inv;
+                g.Y[((size_t)p * a.n_rows + row) * 32 + lane] = y;
+                total[p] += y;
+            }
+            if (lane == 0) g.nrm[row] = nrm;
+        }
+        __syncthreads();
+    }
+    if (warp == 0) {
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+            a.out[((size_t)p * a.n_rows + row) * 32 + lane] = a.relu ? fmaxf(total[p], 0.f) : total[p];
+    }
+}
+
 // y = s / n, n = sqrt(max(|s|^2, eps)):  ds = (dy - y (y . dy)) / n; clamped rows: ds = dy / n
 template <int P>
 __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const L2BwdArgs a) {
@@ -225,6 +293,14 @@ void dispatch_panels(int P, F &&f) {
 
 void launch_node_epilogue(const EpiArgs &a, int P, cudaStream_t s) {
     if (a.n_rows == 0) return;
+    int max_terms = 0;  // longest ordered sum of a row
+    for (int gi = 0; gi < a.n_groups; ++gi)
+        max_terms = std::max(max_terms, a.g[gi].n_peers > 0 ? 1 : a.g[gi].row_seg_ptr != nullptr ? 1 : a.g[gi].n_slots);
+    if (max_terms >= 16 && a.n_rows <= 4096) {
+        dispatch_panels(P, [&](auto tag) { node_epilogue_wide_kernel<decltype(tag)::value><<<a.n_rows, 256, 0, s>>>(a); });
+        CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     dim3 grid((unsigned)((a.n_rows + 7) / 8)), block(256);
     dispatch_panels(P, [&](auto tag) { node_epilogue_kernel<decltype(tag)::value><<<grid, block, 0, s>>>(a); });
     CUDA_CHECK(cudaGetLastError());
