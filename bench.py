@@ -305,6 +305,12 @@ def run_ours(args):
     peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s (B200_PROFILING.md)'
     spmm = {k: v for k, v in phases.items() if k.startswith('spmm_fwd')}
     top = max(spmm, key=lambda k: spmm[k]['ms_per_step'])
+    traffic = None  # DRAM bytes per launch of that kernel from the committed ncu --set full capture (1 GPU, poly shape)
+    try:
+        if world == 1 and args.config == 'poly' and args.scale == 1:
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json'))).get(top)
+    except Exception:
+        pass
     spe = steps_per_epoch(it)
     sps = args.steps / (dev_ms * 1e-3)
     e2e_sps = args.steps / e2e_s
@@ -320,7 +326,7 @@ def run_ours(args):
                 'h2d_bytes_per_step': HYPER['batch_size'] * 2 * 4, 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches),
         'roofline': {'bound': 'hbm', 'kernel': top, 'achieved': spmm[top]['gbs'], 'peak': peak, 'unit': 'GB/s',
-                     'frac': spmm[top]['gbs'] / peak, 'traffic': None, 'peak_source': peak_src,
+                     'frac': spmm[top]['gbs'] / peak, 'traffic': traffic, 'peak_source': peak_src,
                      'algorithmic_bytes': spmm[top]['bytes'], 'ms': spmm[top]['ms_per_step']},
         'kernels': phases,
         'loss_first_last': [float(losses[0]), float(losses[-1])],
