@@ -1040,6 +1040,14 @@ void ensure_batch_capacity(dgn_graph *g, int B) {
     g->ring_cap = B;
 }
 
+// all-pairs scores: tensor cores (tcgen05, 3 x TF32) unless DGN_PREDICT_FFMA=1 asks for the CUDA-core kernel
+void run_predict(dgn_graph *g, const PredictArgs &a) {
+    const char *e = getenv("DGN_PREDICT_FFMA");
+    if (e && e[0] == '1') launch_predict(a, g->stream);
+    else launch_predict_tc(a, g->n_sm, g->stream);
+    g->launches++;
+}
+
 PredictArgs predict_args(dgn_graph *g, int r, int count) {
     DGN_REQUIRE(r >= 0 && r + count <= g->R && count >= 1, "relation range [%d, %d) out of range", r, r + count);
     const int gi = g->flat[r].first, k = g->flat[r].second;
@@ -1680,8 +1688,7 @@ extern "C" int dgn_predict_all_pairs(dgn_graph *g, int r, float *out) {
     float *tmp = dev_alloc<float>(n);
     a.out = tmp;
     try {
-        launch_predict(a, g->stream);
-        g->launches++;
+        run_predict(g, a);
         CUDA_CHECK(cudaStreamSynchronize(g->stream));
         CUDA_CHECK(cudaMemcpy(out, tmp, n * sizeof(float), cudaMemcpyDeviceToHost));
     } catch (...) {
@@ -1700,8 +1707,7 @@ extern "C" int dgn_predict_relations_dev(dgn_graph *g, int r0, int count, float 
     PredictArgs a = predict_args(g, r0, count);
     a.out = out_dev;
     PhaseScope ph(g, "predict");
-    launch_predict(a, g->stream);
-    g->launches++;
+    run_predict(g, a);
     DGN_API_END
 }
 

@@ -241,6 +241,7 @@ void launch_dh(const DenseArgs &a, int D1, int D2, cudaStream_t s);
 void launch_decode(const DecodeArgs &a, cudaStream_t s);
 void launch_fixed_to_float(const long long *q, float *out, size_t n, cudaStream_t s);
 void launch_predict(const PredictArgs &a, cudaStream_t s);
+void launch_predict_tc(const PredictArgs &a, int n_sm, cudaStream_t s);  // tcgen05, 3 x TF32 (predict_tc.cu)
 void launch_predict_edges(const PredictArgs &a, const int *edges, int n_edges, int apply_sigmoid, float *out,
                           cudaStream_t s);
 void launch_adam(float *p, const float *g, float *m, float *v, long long n, float alpha, float one_minus_b1,

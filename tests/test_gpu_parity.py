@@ -204,6 +204,34 @@ def test_predictions(toy_mixed):
         assert rel_err(eglb, glb) <= 1e-7 and rel_err(eloc, loc) <= 1e-7
 
 
+def test_predict_all_relations_tensor_cores(mini, toy_mixed):
+    """BASELINE config #4 in small: every relation of a group in one call (evaluateAll,
+    DecagonAccuracyEvaluator.py:57-91).  The tcgen05 (3 x TF32) kernel against the float64 oracle and against
+    the CUDA-core kernel, on ragged tiles (97 and 400 / 500 nodes are not multiples of the 128-wide tiles)."""
+    import torch
+    for c in (mini, toy_mixed):
+        eng = c.eng
+        Z = check_forward(c, eng, 0.0, 0)
+        for g in c.graph.groups:
+            K = c.graph.K[g]
+            r0 = eng.flat_index[(g, 0)]
+            n_i, n_j = c.graph.n_nodes[g[0]], c.graph.n_nodes[g[1]]
+            outs = {}
+            for mode in ('0', '1'):
+                os.environ['DGN_PREDICT_FFMA'] = mode
+                try:
+                    buf = torch.full((K, n_i, n_j), float('nan'), dtype=torch.float32, device='cuda')
+                    eng.predict_relations_dev(r0, K, buf.data_ptr())
+                    eng.sync()
+                    outs[mode] = buf.cpu().numpy()
+                finally:
+                    del os.environ['DGN_PREDICT_FFMA']
+            for k in range(K):
+                ref = O.predict_all_pairs(c.graph, c.p64, Z, g, k)
+                assert rel_err(outs['0'][k], ref) <= TOL, (g, k)
+                assert rel_err(outs['1'][k], ref) <= TOL, (g, k)
+
+
 def test_param_roundtrip_and_errors(toy):
     eng = toy.eng
     back = eng.get_params()
