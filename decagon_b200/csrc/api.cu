@@ -1739,6 +1739,71 @@ extern "C" int dgn_predict_edges(dgn_graph *g, int r, const int32_t *edges, int3
     DGN_API_END
 }
 
+// evaluateAll in one call: edges of many relations of one group, optional pooled AUROC / AUPRC on the device
+extern "C" int dgn_evaluate_edges(dgn_graph *g, int group, int64_t n_edges, const int32_t *rel_k, const int32_t *edges,
+                                  const uint8_t *labels, int apply_sigmoid, float *scores_out, double *auroc_out,
+                                  double *auprc_out) {
+    DGN_API_BEGIN
+    check_finalized(g);
+    DGN_REQUIRE(group >= 0 && group < (int)g->groups.size(), "group %d out of range", group);
+    DGN_REQUIRE(n_edges >= 0 && (n_edges == 0 || (rel_k && edges)), "null argument");
+    const bool want_auc = auroc_out || auprc_out;
+    DGN_REQUIRE(!want_auc || labels || n_edges == 0, "labels are needed for AUROC / AUPRC");
+    if (auroc_out) *auroc_out = nan("");
+    if (auprc_out) *auprc_out = nan("");
+    if (n_edges == 0) return DGN_OK;
+    CUDA_CHECK(cudaSetDevice(g->device));
+    Group &G = g->groups[group];
+    int r0 = -1;
+    for (int r = 0; r < g->R && r0 < 0; ++r)
+        if (g->flat[r].first == group) r0 = r;
+    PredictArgs a = predict_args(g, r0, 1);
+    for (int64_t e = 0; e < n_edges; ++e) {
+        DGN_REQUIRE(rel_k[e] >= 0 && rel_k[e] < G.K, "edge %lld: relation %d outside group of %d", (long long)e, rel_k[e], G.K);
+        DGN_REQUIRE(edges[2 * e] >= 0 && edges[2 * e] < a.n_i && edges[2 * e + 1] >= 0 && edges[2 * e + 1] < a.n_j,
+                    "edge %lld = (%d, %d) outside %d x %d", (long long)e, edges[2 * e], edges[2 * e + 1], a.n_i, a.n_j);
+    }
+    int *k_dev = nullptr, *e_dev = nullptr;
+    float *s_dev = nullptr, *ss_dev = nullptr;
+    unsigned char *l_dev = nullptr, *sl_dev = nullptr;
+    void *tmp = nullptr;
+    double *res_dev = nullptr;
+    auto release = [&]() {
+        cudaFree(k_dev), cudaFree(e_dev), cudaFree(s_dev), cudaFree(ss_dev), cudaFree(l_dev), cudaFree(sl_dev);
+        cudaFree(tmp), cudaFree(res_dev);
+    };
+    try {
+        PhaseScope ph(g, "evaluate");
+        k_dev = dev_alloc<int>((size_t)n_edges), e_dev = dev_alloc<int>((size_t)n_edges * 2);
+        s_dev = dev_alloc<float>((size_t)n_edges);
+        CUDA_CHECK(cudaMemcpyAsync(k_dev, rel_k, (size_t)n_edges * sizeof(int), cudaMemcpyHostToDevice, g->stream));
+        CUDA_CHECK(cudaMemcpyAsync(e_dev, edges, (size_t)n_edges * 2 * sizeof(int), cudaMemcpyHostToDevice, g->stream));
+        launch_predict_edges_multi(a, k_dev, e_dev, n_edges, apply_sigmoid, s_dev, g->stream);
+        g->launches++;
+        if (scores_out)
+            CUDA_CHECK(cudaMemcpyAsync(scores_out, s_dev, (size_t)n_edges * sizeof(float), cudaMemcpyDeviceToHost, g->stream));
+        double res[4] = {0, 0, 0, 0};
+        if (want_auc) {
+            const size_t tmp_bytes = auc_sort_bytes(n_edges);
+            l_dev = dev_alloc<unsigned char>((size_t)n_edges), sl_dev = dev_alloc<unsigned char>((size_t)n_edges);
+            ss_dev = dev_alloc<float>((size_t)n_edges), res_dev = dev_alloc<double>(4);
+            tmp = dev_alloc<unsigned char>(tmp_bytes ? tmp_bytes : 1);
+            CUDA_CHECK(cudaMemcpyAsync(l_dev, labels, (size_t)n_edges, cudaMemcpyHostToDevice, g->stream));
+            launch_auc(s_dev, l_dev, n_edges, ss_dev, sl_dev, tmp, tmp_bytes, res_dev, g->stream);
+            g->launches += 2;
+            CUDA_CHECK(cudaMemcpyAsync(res, res_dev, sizeof(res), cudaMemcpyDeviceToHost, g->stream));
+        }
+        CUDA_CHECK(cudaStreamSynchronize(g->stream));
+        if (auroc_out) *auroc_out = res[0];
+        if (auprc_out) *auprc_out = res[1];
+    } catch (...) {
+        release();
+        throw;
+    }
+    release();
+    DGN_API_END
+}
+
 extern "C" int dgn_tensor_get(dgn_graph *g, int which, int index, float *out, int64_t n) {
     DGN_API_BEGIN
     check_finalized(g);

@@ -244,6 +244,11 @@ void launch_predict(const PredictArgs &a, cudaStream_t s);
 void launch_predict_tc(const PredictArgs &a, int n_sm, cudaStream_t s);  // tcgen05, 3 x TF32 (predict_tc.cu)
 void launch_predict_edges(const PredictArgs &a, const int *edges, int n_edges, int apply_sigmoid, float *out,
                           cudaStream_t s);
+void launch_predict_edges_multi(const PredictArgs &a, const int *rel_k, const int *edges, long long n_edges,
+                                int apply_sigmoid, float *out, cudaStream_t s);  // evaluate.cu
+size_t auc_sort_bytes(long long n);
+void launch_auc(const float *scores, const unsigned char *labels, long long n, float *sorted_scores,
+                unsigned char *sorted_labels, void *tmp, size_t tmp_bytes, double *out, cudaStream_t s);
 void launch_adam(float *p, const float *g, float *m, float *v, long long n, float alpha, float one_minus_b1,
                  float one_minus_b2, float eps, cudaStream_t s);
 // multi-GPU exchange (node.cu): ordered sum of the local partials into this rank's exchange buffer; then

@@ -4,6 +4,7 @@ This is the layer the TF-style shim (``decagon_b200.session``) and ``bench.py`` 
 method is a thin ctypes call into libdecagon_b200.so -- no arithmetic happens here.
 """
 import ctypes
+import math
 
 import numpy as np
 
@@ -249,6 +250,28 @@ class Engine(object):
         check(self.lib.dgn_predict_edges(self._h, int(r), ptr(edges, ctypes.c_int32), len(edges), 1 if sigmoid else 0,
                                          ptr(out, ctypes.c_float)))
         return out
+
+    def evaluate_edges(self, group, rel_k, edges, labels=None, sigmoid=True, want_scores=True):
+        """Edges of many relations of one group in one launch; with ``labels`` also the pooled AUROC / AUPRC computed
+        on the device.  Returns ``(scores or None, auroc, auprc)`` (DecagonAccuracyEvaluator.py:57-91)."""
+        gi = self.groups.index(tuple(group)) if not isinstance(group, int) else group
+        edges = as_i32(np.asarray(edges).reshape(-1, 2))
+        rel_k = as_i32(np.asarray(rel_k).reshape(-1))
+        if len(rel_k) != len(edges):
+            raise ValueError('rel_k and edges differ in length')
+        scores = np.empty(len(edges), dtype=np.float32) if want_scores else None
+        auroc, auprc = ctypes.c_double(math.nan), ctypes.c_double(math.nan)
+        lab = None
+        if labels is not None:
+            lab = np.ascontiguousarray(np.asarray(labels).reshape(-1) != 0, dtype=np.uint8)
+            if len(lab) != len(edges):
+                raise ValueError('labels and edges differ in length')
+        check(self.lib.dgn_evaluate_edges(
+            self._h, gi, len(edges), ptr(rel_k, ctypes.c_int32), ptr(edges, ctypes.c_int32),
+            ptr(lab, ctypes.c_uint8) if lab is not None else None, 1 if sigmoid else 0,
+            ptr(scores, ctypes.c_float) if want_scores else None,
+            ctypes.byref(auroc) if lab is not None else None, ctypes.byref(auprc) if lab is not None else None))
+        return scores, auroc.value, auprc.value
 
     def tensor(self, which, index):
         if which in (_lib.TENSOR_HIDDEN1, _lib.TENSOR_EMBEDDINGS, _lib.TENSOR_GRAD_EMBEDDINGS):

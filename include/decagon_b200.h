@@ -172,6 +172,16 @@ int dgn_predict_relations_dev(dgn_graph *g, int r0, int count, float *out_dev);
  * materialising P_r on the host */
 int dgn_predict_edges(dgn_graph *g, int r, const int32_t *edges, int32_t n_edges, int apply_sigmoid, float *out);
 
+/* DecagonAccuracyEvaluator.evaluateAll (DecagonAccuracyEvaluator.py:57-91) in one call, after ONE
+ * dgn_encoder_forward: edge e = (rel_k[e], edges[2e], edges[2e+1]) of `group` is scored like dgn_predict_edges
+ * (one launch for all relations); scores_out (host, [n_edges], may be NULL) receives the scores in input order.
+ * With labels (1 = positive, 0 = negative) and auroc_out / auprc_out non-NULL the pooled scores are sorted on
+ * the device and sklearn.metrics.roc_auc_score / average_precision_score (:69-75) are evaluated there
+ * (ties share one threshold; NaN when a class is empty, where sklearn raises ValueError). */
+int dgn_evaluate_edges(dgn_graph *g, int group, int64_t n_edges, const int32_t *rel_k, const int32_t *edges,
+                       const uint8_t *labels, int apply_sigmoid, float *scores_out, double *auroc_out,
+                       double *auprc_out);
+
 /* model.embeddings[t], model.hidden1[t], per-group layer outputs (DecagonLogger.py:239-242) */
 int dgn_tensor_get(dgn_graph *g, int which, int index, float *out, int64_t n);
 

@@ -158,3 +158,89 @@ def test_adjacency_is_uploaded_once():
     fd[key] = (c.copy(), v.copy(), s_)
     sess.run([opt.opt_op, opt.cost, opt.batch_edge_type_idx], feed_dict=fd)
     assert uploads == [minibatch.edge_type2idx[1, 1, 0]]
+
+
+def test_accuracy_evaluator_matches_reference_sequence_and_oracle():
+    """DecagonAccuracyEvaluator.evaluate / evaluateAll (DecagonAccuracyEvaluator.py:57-113): the reference's
+    own sequence (session.run(predictions) per relation + host sigmoid + np.take + sklearn), the batched
+    device path with sklearn, the batched path with device-side AUROC / AUPRC and the float64 oracle."""
+    from sklearn import metrics
+    from decagon_b200.evaluator import DecagonAccuracyEvaluator, sigmoid
+    inputs = datasets.toy_graph()
+    placeholders, minibatch, model, opt = build_trainable(inputs)
+    sess = tf.Session(seed=SEED)
+    sess.run(tf.global_variables_initializer())
+    np.random.seed(1)
+    minibatch.shuffle()
+    for _ in range(8):  # a few steps so the scores are not at their initial scale
+        fd = minibatch.update_feed_dict(minibatch.next_minibatch_feed_dict(placeholders), 0.1, placeholders)
+        sess.run([opt.opt_op, opt.cost, opt.batch_edge_type_idx], feed_dict=fd)
+    feed_dict = minibatch.update_feed_dict(minibatch.next_minibatch_feed_dict(placeholders), 0.1, placeholders)
+    pos, neg = minibatch.val_edges, minibatch.val_edges_false
+    mk = lambda **kw: DecagonAccuracyEvaluator(sess, placeholders, opt.predictions, minibatch.edge_type2idx, **kw)
+    ref_all = mk(fast=False).evaluateAll(dict(feed_dict), pos, neg)
+    host_all = mk(fast=True, device_metrics=False).evaluateAll(dict(feed_dict), pos, neg)
+    dev_all = mk(fast=True, device_metrics=True).evaluateAll(dict(feed_dict), pos, neg)
+    assert ref_all.apk == 0 and 0.0 <= ref_all.auroc <= 1.0
+    for got in (host_all, dev_all):
+        assert abs(got.auroc - ref_all.auroc) < 5e-4 and abs(got.auprc - ref_all.auprc) < 5e-4, (got, ref_all)
+    # same scores -> the device-side metrics equal sklearn's to rounding
+    assert abs(dev_all.auroc - host_all.auroc) < 1e-9 and abs(dev_all.auprc - host_all.auprc) < 1e-9
+
+    rel = (1, 1, 2)
+    one_ref = mk(fast=False).evaluate(dict(feed_dict), rel, pos, neg)
+    one_fast = mk(fast=True).evaluate(dict(feed_dict), rel, pos, neg)
+    assert abs(one_ref.auroc - one_fast.auroc) < 5e-4 and abs(one_ref.auprc - one_fast.auprc) < 5e-4
+
+    # the float64 oracle on the engine's current parameters: AUROC / AUPRC to 3 decimals (BASELINE north_star)
+    eng = model.engine
+    graph = O.Graph.from_iterator(minibatch, inputs.edge_type2decoder)
+    p = O.cast_params(eng.get_params(), np.float64)
+    Z, _ = O.encoder_forward(graph, p)
+    preds, labels = [], []
+    for k in range(inputs.edge_types[1, 1]):
+        P = sigmoid(O.predict_all_pairs(graph, p, Z, (1, 1), k))
+        for edges, lab in ((pos[1, 1][k], 1), (neg[1, 1][k], 0)):
+            e = np.asarray(edges).reshape(-1, 2).astype(np.int64)
+            preds.append(P[e[:, 0], e[:, 1]])
+            labels.append(np.full(len(e), lab))
+    preds, labels = np.hstack(preds), np.hstack(labels)
+    assert round(metrics.roc_auc_score(labels, preds), 3) == round(dev_all.auroc, 3) or \
+        abs(metrics.roc_auc_score(labels, preds) - dev_all.auroc) < 5e-4
+    assert abs(metrics.average_precision_score(labels, preds) - dev_all.auprc) < 5e-4
+
+
+def test_device_auc_with_ties_and_empty_classes():
+    """The device AUROC / AUPRC against sklearn on heavily tied scores (few distinct embedding rows), in input
+    order independent of the pooling, and NaN where sklearn raises (one class only)."""
+    from sklearn import metrics
+    case = common.Case(datasets.toy_graph())
+    eng = case.engine()
+    rng = np.random.RandomState(3)
+    n1 = case.inputs.n_nodes[1]
+    proto = rng.randn(5, 32).astype(np.float32) * 0.4
+    eng.forward(0.0, 0, 0)
+    eng.set_embeddings(1, proto[rng.randint(0, 5, n1)])
+    n = 20000
+    ks = rng.randint(0, case.inputs.edge_types[1, 1], n)
+    edges = rng.randint(0, n1, (n, 2))
+    labels = (rng.rand(n) < 0.3).astype(np.uint8)
+    scores, auroc, auprc = eng.evaluate_edges((1, 1), ks, edges, labels)
+    assert len(np.unique(scores)) < 400  # ties dominate
+    assert abs(auroc - metrics.roc_auc_score(labels, scores)) < 1e-12
+    assert abs(auprc - metrics.average_precision_score(labels, scores)) < 1e-12
+    # per-edge scores are those of the single-relation call
+    r0 = case.it.edge_type2idx[1, 1, 0]
+    sel = ks == 0
+    assert np.array_equal(scores[sel], eng.predict_edges(r0, edges[sel]))
+    # one class only
+    _, a1, p1 = eng.evaluate_edges((1, 1), ks, edges, np.ones(n, dtype=np.uint8))
+    assert np.isnan(a1) and abs(p1 - 1.0) < 1e-12
+    _, a0, p0 = eng.evaluate_edges((1, 1), ks, edges, np.zeros(n, dtype=np.uint8))
+    assert np.isnan(a0) and np.isnan(p0)
+    # empty input
+    s, a, p_ = eng.evaluate_edges((1, 1), np.zeros(0, np.int32), np.zeros((0, 2), np.int32), np.zeros(0, np.uint8))
+    assert len(s) == 0 and np.isnan(a) and np.isnan(p_)
+    with pytest.raises(ValueError):
+        eng.evaluate_edges((1, 1), [99], [[0, 0]], [1])
+    eng.close()
