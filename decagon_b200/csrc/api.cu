@@ -347,6 +347,7 @@ struct Group {
     float *P2 = nullptr, *dS = nullptr, *G2 = nullptr, *bwd_partial = nullptr, *dW2part = nullptr, *dHpart = nullptr;
     uint32_t *mask1 = nullptr, *mask2 = nullptr;
     long long mask1_words = 0, mask2_words = 0;
+    bool dense_tc = false;  // layer-2 contractions on tcgen05 (dense_tc.cu)
     int n_rb = 1, n_rb_pd = 1, slots_proj = 1, slots_dh = 1, slots_dw2 = 1;  // dense layer-2 kernels: row blocks, CTAs per block
     std::vector<uint32_t *> thr;  // per relation
     std::vector<int> thr_n;
@@ -603,12 +604,24 @@ void build_group(dgn_graph *g, Group &G) {
     G.mask2 = dev_alloc<uint32_t>((size_t)G.mask2_words);
 
     // dense layer-2 kernels: persistent CTAs, one per (row block, slot of relations)
-    const int RB = dense_row_block(g->d1, 1), RBpd = dense_row_block(g->d1, 0);
-    G.n_rb = (n_j + RB - 1) / RB;        // dw2
-    G.n_rb_pd = (n_j + RBpd - 1) / RBpd;  // project, dh
-    G.slots_dw2 = std::max(1, std::min(K, g->n_sm / G.n_rb));
-    G.slots_proj = std::max(1, std::min(K, g->n_sm / G.n_rb_pd));
-    G.slots_dh = std::max(1, std::min(K, g->n_sm / (P1 * G.n_rb_pd)));
+    // tensor-core versions (dense_tc.cu) unless DGN_DENSE_FFMA=1 asks for the CUDA-core kernels of dense.cu
+    const char *ffma = getenv("DGN_DENSE_FFMA");
+    G.dense_tc = dense_tc_supported(g->d1, g->d2) && !(ffma && ffma[0] == '1');
+    if (G.dense_tc) {
+        const int n_rt = dense_tc_tiles(n_j);  // row tiles of 128 = threads of a CTA, two CTAs per SM
+        G.n_rb_pd = n_rt;
+        G.slots_proj = G.slots_dh = std::max(1, std::min(K, 2 * g->n_sm / n_rt));
+        // dw2: CTA = (relation, chunk of row tiles); partials per chunk when the relations alone cannot fill the GPU
+        G.n_rb = K >= 2 * g->n_sm ? 1 : std::max(1, std::min(n_rt, (2 * g->n_sm + K - 1) / std::max(K, 1)));
+        G.slots_dw2 = 1;
+    } else {
+        const int RB = dense_row_block(g->d1, 1), RBpd = dense_row_block(g->d1, 0);
+        G.n_rb = (n_j + RB - 1) / RB;        // dw2
+        G.n_rb_pd = (n_j + RBpd - 1) / RBpd;  // project, dh
+        G.slots_dw2 = std::max(1, std::min(K, g->n_sm / G.n_rb));
+        G.slots_proj = std::max(1, std::min(K, g->n_sm / G.n_rb_pd));
+        G.slots_dh = std::max(1, std::min(K, g->n_sm / (P1 * G.n_rb_pd)));
+    }
     if (G.n_rb > 1) G.dW2part = dev_alloc<float>((size_t)K * G.n_rb * g->d1 * g->d2);
     G.dHpart = dev_alloc<float>((size_t)G.slots_dh * panel_floats(P1, n_j));
 }
@@ -785,7 +798,8 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step, StepDep
             a.H = g->types[G.j].H, a.W2 = g->params + G.w2_off, a.P2 = G.P2;
             a.mask = drop ? G.mask2 : nullptr, a.scale = scale, a.K = G.Kl, a.n_j = G.n_j;
             a.n_rb = G.n_rb_pd, a.n_slots = G.slots_proj;
-            launch_project(a, g->d1, g->d2, lane_stream(g, G.lane));
+            if (G.dense_tc) launch_project_tc(a, g->d1, lane_stream(g, G.lane));
+            else launch_project(a, g->d1, g->d2, lane_stream(g, G.lane));
             g->launches++;
         }
         {
@@ -871,7 +885,8 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam) {
         {
             PhaseScope ph(g, "dw2", gi, G.lane);
             a.n_slots = G.slots_dw2;
-            launch_dw2(a, g->d1, g->d2, s);
+            if (G.dense_tc) launch_dw2_tc(a, g->d1, s);
+            else launch_dw2(a, g->d1, g->d2, s);
             g->launches++;
             if (G.n_rb > 1) {
                 launch_dw2_reduce(G.dW2part, g->grads + G.w2_off, G.Kl, G.n_rb, g->d1 * g->d2, s);
@@ -881,7 +896,8 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam) {
         {
             PhaseScope ph(g, "dh", gi, G.lane);
             a.n_slots = G.slots_dh, a.n_rb = G.n_rb_pd;
-            launch_dh(a, g->d1, g->d2, s);
+            if (G.dense_tc) launch_dh_tc(a, g->d1, s);
+            else launch_dh(a, g->d1, g->d2, s);
             g->launches++;
             if (G.partitioned) exchange(g, G, 2, G.dHpart, G.slots_dh, s);
         }

@@ -238,6 +238,12 @@ void launch_project(const DenseArgs &a, int D1, int D2, cudaStream_t s);
 void launch_dw2(const DenseArgs &a, int D1, int D2, cudaStream_t s);
 void launch_dw2_reduce(const float *part, float *out, int K, int n_chunks, int elems, cudaStream_t s);
 void launch_dh(const DenseArgs &a, int D1, int D2, cudaStream_t s);
+// tcgen05 versions (dense_tc.cu): a.n_rb = row tiles of 128 (project, dh) / chunks of row tiles per relation (dw2)
+bool dense_tc_supported(int D1, int D2);
+int dense_tc_tiles(int n_j);
+void launch_project_tc(const DenseArgs &a, int D1, cudaStream_t s);
+void launch_dw2_tc(const DenseArgs &a, int D1, cudaStream_t s);
+void launch_dh_tc(const DenseArgs &a, int D1, cudaStream_t s);
 void launch_decode(const DecodeArgs &a, cudaStream_t s);
 void launch_fixed_to_float(const long long *q, float *out, size_t n, cudaStream_t s);
 void launch_predict(const PredictArgs &a, cudaStream_t s);

@@ -15,15 +15,24 @@ __device__ __forceinline__ uint32_t sw128(int row, int chunk) {
 }
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in [0,14), leading byte offset >> 4
-// in [16,30) (unused for swizzled K-major: 1), stride byte offset >> 4 in [32,46) (1024 B between 8-row groups),
-// version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).  One k-step of 8 tf32 = 32 bytes = + 2 encoded.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3fff) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+// in [16,30), stride byte offset >> 4 in [32,46), version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
+// K-major operand (row = one M / N index, 128 B = 32 tf32 of K): LBO unused (1), SBO = 1024 B between 8-row groups;
+// one k-step of 8 tf32 = 32 bytes = + 2 in the encoded start address.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes = 16, uint32_t sbo_bytes = 1024) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46) | (2ull << 61);
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 at [4,6)), A = B = TF32 (2 at [7,10), [10,13)), both
-// K-major (0 at bits 15, 16), N >> 3 at [17,23), M >> 4 at [24,29)
-constexpr uint32_t idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// MN-major operand (cute: Swizzle<3,4,3> o ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO))): an atom is 8 K-rows of 128 bytes, a row
+// = 32 consecutive M / N indices at one K; the 16-byte chunk index is XORed with the row index inside the atom
+// exactly as in the K-major tile.  LBO = bytes between atoms along M / N, SBO = bytes between atoms along K; one
+// k-step of 8 tf32 is exactly one atom row group, so successive k-steps use successive descriptors.
+__device__ __forceinline__ uint32_t mn_off(int k_row, int chunk) { return (uint32_t)((k_row & 7) * 128 + ((chunk ^ (k_row & 7)) << 4)); }
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 at [4,6)), A = B = TF32 (2 at [7,10), [10,13)),
+// A / B major at bits 15 / 16 (0 = K-major, 1 = MN-major), N >> 3 at [17,23), M >> 4 at [24,29)
+constexpr uint32_t idesc_tf32(int M, int N, int a_mn = 0, int b_mn = 0) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {

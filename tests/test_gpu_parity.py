@@ -255,3 +255,26 @@ def test_hidden_sizes():
         r, batch = c.batches(1)[0]
         check_grads(c, eng, r, batch, 0.1, 0, 'hinge')
         eng.close()
+
+
+@pytest.mark.parametrize('h1', [32, 64])
+def test_dense_layer2_tensor_cores_match_cuda_cores(h1):
+    """project / dw2 / dh on tcgen05 (TF32 split, dense_tc.cu; the default) and on the CUDA cores
+    (DGN_DENSE_FFMA=1, dense.cu): both against the float64 oracle, dropout on and off, on a graph whose node
+    counts leave ragged 128-row tiles (300 and 97 rows)."""
+    c = Case(common.mini_poly(n_types=9, seed=40 + h1), batch_size=64, hidden1=h1)
+    os.environ['DGN_DENSE_FFMA'] = '1'
+    try:
+        ffma = c.engine()
+    finally:
+        del os.environ['DGN_DENSE_FFMA']
+    tcore = c.engine()
+    for rate in (0.0, 0.1):
+        for eng in (ffma, tcore):
+            check_forward(c, eng, rate, 0)
+            for step, (r, batch) in enumerate(c.batches(3)):
+                check_grads(c, eng, r, batch, rate, step, 'hinge')
+        for t in c.graph.n_nodes:
+            assert rel_err(tcore.embeddings(t), ffma.embeddings(t)) <= TOL
+    ffma.close()
+    tcore.close()
