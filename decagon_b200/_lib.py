@@ -64,6 +64,8 @@ SIGNATURES = {
     'dgn_timing_enable': (ctypes.c_int, [c_graph, ctypes.c_int]),
     'dgn_timing_reset': (ctypes.c_int, [c_graph]),
     'dgn_timing_get': (ctypes.c_int, [c_graph, ctypes.c_char_p, c_f64p, c_i64p]),
+    'dgn_timeline_get': (ctypes.c_int, [c_graph, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                        c_f64p, c_f64p]),
     'dgn_launch_count': (ctypes.c_int, [c_graph, c_i64p]),
     'dgn_timer_start': (ctypes.c_int, [c_graph]),
     'dgn_timer_stop': (ctypes.c_int, [c_graph, c_f64p]),

@@ -356,6 +356,7 @@ struct Group {
 struct Phase {
     std::string name;
     cudaEvent_t start, stop;
+    int lane = 0;
 };
 
 }  // namespace
@@ -420,6 +421,7 @@ struct PhaseScope {
         Phase p;
         p.name = name;
         if (group >= 0) p.name += "/g" + std::to_string(group);
+        p.lane = lane;
         CUDA_CHECK(cudaEventCreate(&p.start));
         CUDA_CHECK(cudaEventCreate(&p.stop));
         CUDA_CHECK(cudaEventRecord(p.start, st));
@@ -613,7 +615,7 @@ void build_group(dgn_graph *g, Group &G) {
         G.slots_proj = G.slots_dh = std::max(1, std::min(K, 2 * g->n_sm / n_rt));
         // dw2: CTA = (relation, chunk of row tiles); partials per chunk when the relations alone cannot fill the GPU
         G.n_rb = K >= 2 * g->n_sm ? 1 : std::max(1, std::min(n_rt, (2 * g->n_sm + K - 1) / std::max(K, 1)));
-        G.slots_dw2 = 1;
+        G.slots_dw2 = 2 * g->n_sm;  // persistent CTAs
     } else {
         const int RB = dense_row_block(g->d1, 1), RBpd = dense_row_block(g->d1, 0);
         G.n_rb = (n_j + RB - 1) / RB;        // dw2
@@ -688,6 +690,22 @@ const float *peer_ptr(dgn_graph *g, const Group &G, int x, int r) {
     return reinterpret_cast<const float *>(g->peer_comm[r] + X.off) + (X.stamp & 1) * X.floats;
 }
 
+// Issue order of the groups: lane 0 first; on lane 1 the groups that lane 0 waits for first (row type on lane 0 in
+// the forward pass and the layer-1 backward, column type on lane 0 in the layer-2 backward).
+std::vector<int> lane_order(dgn_graph *g, bool by_col_type) {
+    std::vector<int> order;
+    for (int gi = 0; gi < g->n_groups; ++gi)
+        if (g->groups[gi].lane == 0) order.push_back(gi);
+    for (int pass = 0; pass < 2; ++pass)
+        for (int gi = 0; gi < g->n_groups; ++gi) {
+            const Group &G = g->groups[gi];
+            if (G.lane != 1) continue;
+            const int t = by_col_type ? G.j : G.i;
+            if ((g->types[t].lane == 0) == (pass == 0)) order.push_back(gi);
+        }
+    return order;
+}
+
 // Per-step dependency state: one Dep per tensor that crosses lanes.
 struct StepDeps {
     std::vector<Dep> S1, S2, dH;   // per group: layer-1 / layer-2 partial sums, dH partials
@@ -709,8 +727,9 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step, StepDep
             PhaseScope ph(g, "mask", -1, G.lane);
             cudaStream_t s = lane_stream(g, G.lane);
             launch_gen_mask(G.mask1, G.mask1_words, G.F_j, 0, G.rel_ids, kStreamDropout1, step, seed, thr, s);
+            g->launches++;
             launch_gen_mask(G.mask2, G.mask2_words, (long long)G.n_j * g->d1, G.n_j * P1, G.rel_ids, kStreamDropout2, step, seed, thr, s);
-            g->launches += 2;
+            g->launches++;
         }
     }
     auto spmm_fwd = [&](Group &G, const float *op, int P, long long op_rows, float *part, const SlotTable &slots,
@@ -772,11 +791,9 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step, StepDep
         g->launches++;
         produced(g, layer == 1 ? D.H[t] : D.Z[t], T.lane);
     };
-    // lane 0 groups first: their kernels are the long ones
-    std::vector<int> order;
-    for (int lane = 0; lane < 2; ++lane)
-        for (int gi = 0; gi < g->n_groups; ++gi)
-            if (g->groups[gi].lane == lane) order.push_back(gi);
+    // lane 0 groups first: their kernels are the long ones.  On lane 1 the groups whose ROW type is summed on lane 0
+    // come first: lane 0 waits for exactly those partial sums before it can go on
+    const std::vector<int> order = lane_order(g, false);
     for (int gi : order) {
         Group &G = g->groups[gi];
         {
@@ -856,12 +873,26 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam) {
             g->launches++;
         }
     };
-    std::vector<int> order;
-    for (int lane = 0; lane < 2; ++lane)
-        for (int gi = 0; gi < g->n_groups; ++gi)
-            if (g->groups[gi].lane == lane) order.push_back(gi);
+    // backward of layer 2: on lane 1 the groups whose COLUMN type is summed on lane 0 come first (lane 0 waits for
+    // their dH partials); backward of layer 1: any order
+    const std::vector<int> order = lane_order(g, false), order2 = lane_order(g, true);
+    std::vector<std::pair<int, DenseArgs>> deferred_dw2;
+    auto run_dw2 = [&](int gi, DenseArgs a) {
+        Group &G = g->groups[gi];
+        cudaStream_t s = lane_stream(g, G.lane);
+        PhaseScope ph(g, "dw2", gi, G.lane);
+        a.n_rb = G.n_rb;
+        a.n_slots = G.slots_dw2;
+        if (G.dense_tc) launch_dw2_tc(a, g->d1, s);
+        else launch_dw2(a, g->d1, g->d2, s);
+        g->launches++;
+        if (G.n_rb > 1) {
+            launch_dw2_reduce(G.dW2part, g->grads + G.w2_off, G.Kl, G.n_rb, g->d1 * g->d2, s);
+            g->launches++;
+        }
+    };
     // ---- layer 2
-    for (int gi : order) {
+    for (int gi : order2) {
         Group &G = g->groups[gi];
         cudaStream_t s = lane_stream(g, G.lane);
         consume(g, D.dZ[G.i], G.lane);
@@ -882,17 +913,10 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam) {
         a.n_rb = G.n_rb;
         a.dW2 = G.n_rb > 1 ? G.dW2part : g->grads + G.w2_off;
         a.dHpart = G.dHpart;
-        {
-            PhaseScope ph(g, "dw2", gi, G.lane);
-            a.n_slots = G.slots_dw2;
-            if (G.dense_tc) launch_dw2_tc(a, g->d1, s);
-            else launch_dw2(a, g->d1, g->d2, s);
-            g->launches++;
-            if (G.n_rb > 1) {
-                launch_dw2_reduce(G.dW2part, g->grads + G.w2_off, G.Kl, G.n_rb, g->d1 * g->d2, s);
-                g->launches++;
-            }
-        }
+        // dW2 of a lane-0 group feeds nothing but Adam: it is queued behind the group's layer-1 backward, where its
+        // tensor-core kernel (which leaves room on the SMs) runs beside lane 1's remaining kernels
+        if (g->two_lanes && G.lane == 0 && G.dense_tc) deferred_dw2.push_back({gi, a});
+        else run_dw2(gi, a);
         {
             PhaseScope ph(g, "dh", gi, G.lane);
             a.n_slots = G.slots_dh, a.n_rb = G.n_rb_pd;
@@ -940,6 +964,7 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam) {
         PhaseScope ph(g, "spmm_bwd1", gi, G.lane);
         spmm_bwd(G, P1, g->grads + G.w1_off, (long long)G.Kl * G.F_j, drop ? G.mask1 : nullptr, adam.alpha != 0.f && G.tstaged && g->fuse_adam);
     }
+    for (auto &d : deferred_dw2) run_dw2(d.first, d.second);
     join_lanes(g, false);
 }
 
@@ -1939,6 +1964,23 @@ extern "C" int dgn_timing_get(dgn_graph *g, const char *name, double *ms_out, in
         }
     *ms_out = total;
     if (count_out) *count_out = count;
+    DGN_API_END
+}
+
+// phase `index` of the recorded list: name, stream lane and start / stop in ms after the first recorded phase began
+extern "C" int dgn_timeline_get(dgn_graph *g, int index, char *name_out, int name_cap, int *lane_out, double *start_ms_out,
+                                double *stop_ms_out) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(g && name_out && name_cap > 0 && lane_out && start_ms_out && stop_ms_out, "null argument");
+    if (index < 0 || index >= (int)g->phases.size()) return DGN_ERR_INVALID;
+    CUDA_CHECK(cudaSetDevice(g->device));
+    CUDA_CHECK(cudaDeviceSynchronize());
+    const Phase &p = g->phases[index];
+    float a = 0.f, b = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&a, g->phases[0].start, p.start));
+    CUDA_CHECK(cudaEventElapsedTime(&b, g->phases[0].start, p.stop));
+    snprintf(name_out, (size_t)name_cap, "%s", p.name.c_str());
+    *lane_out = p.lane, *start_ms_out = a, *stop_ms_out = b;
     DGN_API_END
 }
 

@@ -54,17 +54,20 @@ __device__ __forceinline__ uint32_t tc_prologue(uint32_t *tmem_slot, uint64_t *b
 }
 
 // ------------------------------------------------------------------------------ P2 = Hm W2
-// CTA = (row tile, slot of relations).  smem: A [KB][hi, lo][128 x 128 B], B [KB][64 x 128 B]
+// CTA = (row tile, slot of relations).  smem: A [KB][hi, lo][128 x 128 B] K-major (thread = its own row, masked),
+// B [D1 / 8 k-blocks][hi, lo atoms of 8 x 128 B] MN-major: W2_k is [D1][32] row-major, i.e. N-contiguous, and is
+// copied as it lies.  The next relation's keep words and W2 are loaded right after the tiles are written, so
+// they fly during the MMAs and the read-back.
 template <int D1>
 __global__ void __launch_bounds__(kThreads, 2) project_tc_kernel(const DenseArgs a) {
-    constexpr int KB = D1 / 32;
-    constexpr uint32_t kIdesc = idesc_tf32(128, 64);
+    constexpr int KB = D1 / 32, NW = D1 / 16;
+    constexpr uint32_t kIdesc = idesc_tf32(128, 64, 0, 1);
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *As = smem;
     unsigned char *Bs = smem + KB * 2 * 16384;
     __shared__ __align__(8) uint64_t mma_done;
     __shared__ uint32_t tmem_slot;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const int rt = blockIdx.x % a.n_rb, slot = blockIdx.x / a.n_rb;
     const int row = rt * kTile + tid;
     const bool valid = row < a.n_j;
@@ -79,25 +82,29 @@ __global__ void __launch_bounds__(kThreads, 2) project_tc_kernel(const DenseArgs
         for (int c = 0; c < 8; ++c) x[p][c] = valid ? ld4(a.H + ((size_t)p * a.n_j + row) * 32 + 4 * c) : zero4();
     const float sc = a.mask != nullptr ? a.scale : 1.f;
     uint32_t parity = 0;
-
-    for (int k = k_begin; k < k_end; ++k) {
-        uint32_t mk[KB];
+    uint32_t mk[KB];
+    float4 w[NW];
+    auto fetch = [&](int k) {
 #pragma unroll
         for (int p = 0; p < KB; ++p)
             mk[p] = (a.mask != nullptr && valid) ? __ldg(a.mask + ((size_t)k * a.n_j + row) * KB + p) : 0xffffffffu;
-        // B: thread (n = lane, 4 consecutive m): W2_k[4 mc + j][n] -> row n (hi) / 32 + n (lo), chunk mc
         const float *W = a.W2 + (size_t)k * D1 * kD2;
 #pragma unroll
-        for (int i = 0; i < D1 / 16; ++i) {
-            const int mc = warp + 4 * i, kb = mc >> 3, c = mc & 7;
-            float4 w, hi, lo;
-            w.x = __ldg(W + (4 * mc + 0) * kD2 + lane), w.y = __ldg(W + (4 * mc + 1) * kD2 + lane);
-            w.z = __ldg(W + (4 * mc + 2) * kD2 + lane), w.w = __ldg(W + (4 * mc + 3) * kD2 + lane);
-            split4(w, hi, lo);
-            st128(Bs + kb * 8192 + sw128(lane, c), hi);
-            st128(Bs + kb * 8192 + sw128(32 + lane, c), lo);
+        for (int j = 0; j < NW; ++j) w[j] = ld4(W + 4 * (tid + kThreads * j));
+    };
+    if (k_begin < k_end) fetch(k_begin);
+
+    for (int k = k_begin; k < k_end; ++k) {
+        // B: float4 i of W2_k = (K index m = i >> 3, N chunk c = i & 7)
+#pragma unroll
+        for (int j = 0; j < NW; ++j) {
+            const int i = tid + kThreads * j, m = i >> 3, c = i & 7;
+            float4 hi, lo;
+            split4(w[j], hi, lo);
+            unsigned char *atom = Bs + (m >> 3) * 2048 + mn_off(m, c);
+            st128(atom, hi);
+            st128(atom + 1024, lo);
         }
-        // A: this thread's row, masked
 #pragma unroll
         for (int p = 0; p < KB; ++p)
 #pragma unroll
@@ -110,6 +117,7 @@ __global__ void __launch_bounds__(kThreads, 2) project_tc_kernel(const DenseArgs
                 st128(As + (p * 2 + 0) * 16384 + off, hi);
                 st128(As + (p * 2 + 1) * 16384 + off, lo);
             }
+        if (k + 1 < k_end) fetch(k + 1);
         fence_async_smem();
         fence_before();
         __syncthreads();
@@ -118,11 +126,11 @@ __global__ void __launch_bounds__(kThreads, 2) project_tc_kernel(const DenseArgs
 #pragma unroll
             for (int p = 0; p < KB; ++p) {
                 const uint64_t ahi = umma_desc(smem_u32(As + (p * 2 + 0) * 16384)), alo = umma_desc(smem_u32(As + (p * 2 + 1) * 16384));
-                const uint64_t b = umma_desc(smem_u32(Bs + p * 8192));
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
-                    mma_tf32(tmem, ahi + 2 * ks, b + 2 * ks, kIdesc, (p | ks) != 0);
-                    mma_tf32(tmem, alo + 2 * ks, b + 2 * ks, kIdesc, 1);
+                    const uint64_t b = umma_desc_mn(smem_u32(Bs + (p * 4 + ks) * 2048), 1024);
+                    mma_tf32(tmem, ahi + 2 * ks, b, kIdesc, (p | ks) != 0);
+                    mma_tf32(tmem, alo + 2 * ks, b, kIdesc, 1);
                 }
             }
             mma_commit(&mma_done);
@@ -151,10 +159,11 @@ __global__ void __launch_bounds__(kThreads, 2) project_tc_kernel(const DenseArgs
 }
 
 // ------------------------------------------------------------------------------ dH += (G2 W2^T) (.) m
-// CTA = (row tile, slot of relations).  smem: A hi, lo [128 x 128 B] (G2 rows), B [2 D1 x 128 B] (W2 hi ; lo)
+// CTA = (row tile, slot of relations).  smem: A hi, lo [128 x 128 B] (G2 rows, K-major), B [2 D1 x 128 B] (W2 hi ; lo,
+// K-major as it lies).  Loads are coalesced (8 lanes = one 128-byte row) and one relation ahead.
 template <int D1>
 __global__ void __launch_bounds__(kThreads, 2) dh_tc_kernel(const DenseArgs a) {
-    constexpr int KB = D1 / 32, N = 2 * D1;
+    constexpr int KB = D1 / 32, N = 2 * D1, NW = D1 / 16;
     constexpr uint32_t kIdesc = idesc_tf32(128, N);
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *Ahi = smem, *Alo = smem + 16384, *Bs = smem + 32768;
@@ -162,8 +171,9 @@ __global__ void __launch_bounds__(kThreads, 2) dh_tc_kernel(const DenseArgs a) {
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int rt = blockIdx.x % a.n_rb, slot = blockIdx.x / a.n_rb;
-    const int row = rt * kTile + tid;
+    const int row = rt * kTile + tid;  // the row this thread reads back from TMEM
     const bool valid = row < a.n_j;
+    const int lrow = tid >> 3, lc = tid & 7;  // loads: rows lrow + 16 i, 16-byte chunk lc
     int k_begin, k_end;
     slot_range(slot, a.n_slots, a.K, k_begin, k_end);
     const uint32_t tmem = tc_prologue<(uint32_t)N>(&tmem_slot, &mma_done, smem);
@@ -174,30 +184,43 @@ __global__ void __launch_bounds__(kThreads, 2) dh_tc_kernel(const DenseArgs a) {
 #pragma unroll
         for (int f = 0; f < 32; ++f) acc[p][f] = 0.f;
     uint32_t parity = 0;
-
-    for (int k = k_begin; k < k_end; ++k) {
-        uint32_t mk[KB];
+    uint32_t mk[KB], mkn[KB];
+    float4 gq[8], w[NW];
+    auto fetch = [&](int k) {
 #pragma unroll
         for (int p = 0; p < KB; ++p)
-            mk[p] = (a.mask != nullptr && valid) ? __ldg(a.mask + ((size_t)k * a.n_j + row) * KB + p) : 0xffffffffu;
-        const float *grow = a.G2 + ((size_t)k * a.n_j + row) * kD2;
+            mkn[p] = (a.mask != nullptr && valid) ? __ldg(a.mask + ((size_t)k * a.n_j + row) * KB + p) : 0xffffffffu;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float4 hi, lo;
-            split4(valid ? ld4(grow + 4 * c) : zero4(), hi, lo);
-            const uint32_t off = sw128(tid, c);
-            st128(Ahi + off, hi);
-            st128(Alo + off, lo);
+        for (int i = 0; i < 8; ++i) {
+            const int r = rt * kTile + lrow + 16 * i;
+            gq[i] = r < a.n_j ? ld4(a.G2 + ((size_t)k * a.n_j + r) * kD2 + 4 * lc) : zero4();
         }
         const float *W = a.W2 + (size_t)k * D1 * kD2;
 #pragma unroll
-        for (int j = 0; j < D1 / 16; ++j) {
+        for (int j = 0; j < NW; ++j) w[j] = ld4(W + 4 * (tid + kThreads * j));
+    };
+    if (k_begin < k_end) fetch(k_begin);
+
+    for (int k = k_begin; k < k_end; ++k) {
+#pragma unroll
+        for (int p = 0; p < KB; ++p) mk[p] = mkn[p];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float4 hi, lo;
+            split4(gq[i], hi, lo);
+            const uint32_t off = sw128(lrow + 16 * i, lc);
+            st128(Ahi + off, hi);
+            st128(Alo + off, lo);
+        }
+#pragma unroll
+        for (int j = 0; j < NW; ++j) {
             const int i = tid + kThreads * j, m = i >> 3, c = i & 7;
             float4 hi, lo;
-            split4(ld4(W + 4 * i), hi, lo);
+            split4(w[j], hi, lo);
             st128(Bs + sw128(m, c), hi);
             st128(Bs + sw128(D1 + m, c), lo);
         }
+        if (k + 1 < k_end) fetch(k + 1);
         fence_async_smem();
         fence_before();
         __syncthreads();
@@ -243,98 +266,52 @@ __global__ void __launch_bounds__(kThreads, 2) dh_tc_kernel(const DenseArgs a) {
 }
 
 // ------------------------------------------------------------------------------ dW2 = Hm^T G2
-// CTA = (relation, chunk of row tiles): the [D1, 32] result accumulates in TMEM over the chunk's row tiles.
-// smem: A [4 kb][128 x 128 B] (rows = features: hi at m, lo at 64 + m; K = the tile's 128 node rows, 32 per
-// k-block = one warp), B [4 kb][64 x 128 B] (rows = n: hi at n, lo at 32 + n).  Both are transposed on the way in:
-// lane = K position, so one scalar store per (feature, lane) and the 32 lanes of a store hit 32 banks.
+// Persistent CTAs over units (relation, chunk of row tiles); the [D1, 32] result of a unit accumulates in TMEM over
+// the unit's row tiles.  Both operands are MN-major, i.e. they are written the way H and G2 lie in memory (a node
+// row = one K index, 32 features / columns = 128 contiguous bytes):
+//   A [16 k-blocks of 8 nodes][4 atoms: hi panel 0, hi panel 1, lo panel 0, lo panel 1]  (M = 128, lo rows at 64 + m)
+//   B [16 k-blocks of 8 nodes][2 atoms: hi, lo]                                           (N = 64)
+// Loads are coalesced and one row tile ahead (issued right after the tiles of the current one are written); the
+// read-back of a finished unit happens after the wait that precedes the next tile's writes.
 template <int D1>
 __global__ void __launch_bounds__(kThreads, 2) dw2_tc_kernel(const DenseArgs a, int n_tiles) {
     constexpr int KB = D1 / 32;
-    constexpr uint32_t kIdesc = idesc_tf32(128, 64);
+    constexpr uint32_t kIdesc = idesc_tf32(128, 64, 1, 1);
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char *As = smem;            // 4 x 16384
-    unsigned char *Bs = smem + 65536;    // 4 x 8192
+    unsigned char *As = smem;            // 16 x 4096
+    unsigned char *Bs = smem + 65536;    // 16 x 2048
     float *stage = reinterpret_cast<float *>(smem + 65536 + 32768);  // [64][33]
     __shared__ __align__(8) uint64_t mma_done;
     __shared__ uint32_t tmem_slot;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const int n_chunks = a.n_rb;
-    const int k = blockIdx.x / n_chunks, chunk = blockIdx.x % n_chunks;
-    const int t_begin = (int)((long long)chunk * n_tiles / n_chunks), t_end = (int)((long long)(chunk + 1) * n_tiles / n_chunks);
-    if (D1 < 64) {  // feature rows D1 .. 63 and 64 + D1 .. 127 of A are never written: they must read as zero
+    const int n_units = a.K * n_chunks;
+    const int u_begin = (int)((long long)blockIdx.x * n_units / gridDim.x), u_end = (int)((long long)(blockIdx.x + 1) * n_units / gridDim.x);
+    if (D1 < 64) {  // the atoms of panel 1 are never written: they must read as zero
         for (int i = tid; i < 65536 / 16; i += kThreads) st128(As + 16 * i, zero4());
     }
     const uint32_t tmem = tc_prologue<64>(&tmem_slot, &mma_done, smem);
+    const int lrow = tid >> 3, lc = tid & 7;      // loads: rows lrow + 16 i of the tile, 16-byte chunk lc
+    const uint32_t toff = mn_off(lrow, lc);       // (lrow + 16 i) & 7 == lrow & 7
+    const float sc = a.mask != nullptr ? a.scale : 1.f;
 
-    // byte offset inside a row group for row-in-group i at this lane's K position
-    uint32_t xo[8];
+    uint32_t mk[KB][8];
+    float4 h[KB][8], gv[8];
+    auto fetch = [&](int k, int t) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) xo[i] = (uint32_t)(i * 128 + (((lane >> 2) ^ i) << 4) + (lane & 3) * 4);
-    unsigned char *Aw = As + warp * 16384, *Bw = Bs + warp * 8192;
-    uint32_t parity = 0;
-    bool pending = false;
-
-    for (int t = t_begin; t < t_end; ++t) {
-        const int row = t * kTile + tid;
-        const bool valid = row < a.n_j;
-        uint32_t mk[KB];
-        float4 h[KB][8], gv[8];
+        for (int i = 0; i < 8; ++i) {
+            const int r = t * kTile + lrow + 16 * i;
+            const bool ok = r < a.n_j;
 #pragma unroll
-        for (int p = 0; p < KB; ++p) {
-            mk[p] = (a.mask != nullptr && valid) ? __ldg(a.mask + ((size_t)k * a.n_j + row) * KB + p) : 0xffffffffu;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) h[p][c] = valid ? ld4(a.H + ((size_t)p * a.n_j + row) * 32 + 4 * c) : zero4();
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) gv[c] = valid ? ld4(a.G2 + ((size_t)k * a.n_j + row) * kD2 + 4 * c) : zero4();
-        if (pending) {  // the previous tile's MMAs still read the operand tiles
-            mbar_wait(&mma_done, parity);
-            parity ^= 1;
-            fence_after();
-        }
-#pragma unroll
-        for (int p = 0; p < KB; ++p)
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                float4 v, hi, lo;
-                v.x = sel(mk[p], 4 * c + 0, h[p][c].x), v.y = sel(mk[p], 4 * c + 1, h[p][c].y);
-                v.z = sel(mk[p], 4 * c + 2, h[p][c].z), v.w = sel(mk[p], 4 * c + 3, h[p][c].w);
-                split4(v, hi, lo);
-                // features m = 32 p + 4 c + j: row group (m >> 3) = 4 p + (c >> 1), row in group 4 (c & 1) + j
-                unsigned char *g_hi = Aw + (4 * p + (c >> 1)) * 1024, *g_lo = g_hi + 8 * 1024;
-                const int i0 = 4 * (c & 1);
-                st32(g_hi + xo[i0 + 0], hi.x), st32(g_hi + xo[i0 + 1], hi.y), st32(g_hi + xo[i0 + 2], hi.z), st32(g_hi + xo[i0 + 3], hi.w);
-                st32(g_lo + xo[i0 + 0], lo.x), st32(g_lo + xo[i0 + 1], lo.y), st32(g_lo + xo[i0 + 2], lo.z), st32(g_lo + xo[i0 + 3], lo.w);
+            for (int p = 0; p < KB; ++p) {
+                mk[p][i] = (a.mask != nullptr && ok) ? __ldg(a.mask + ((size_t)k * a.n_j + r) * KB + p) : 0xffffffffu;
+                h[p][i] = ok ? ld4(a.H + ((size_t)p * a.n_j + r) * 32 + 4 * lc) : zero4();
             }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float4 hi, lo;
-            split4(gv[c], hi, lo);
-            unsigned char *g_hi = Bw + (c >> 1) * 1024, *g_lo = g_hi + 4 * 1024;
-            const int i0 = 4 * (c & 1);
-            st32(g_hi + xo[i0 + 0], hi.x), st32(g_hi + xo[i0 + 1], hi.y), st32(g_hi + xo[i0 + 2], hi.z), st32(g_hi + xo[i0 + 3], hi.w);
-            st32(g_lo + xo[i0 + 0], lo.x), st32(g_lo + xo[i0 + 1], lo.y), st32(g_lo + xo[i0 + 2], lo.z), st32(g_lo + xo[i0 + 3], lo.w);
+            gv[i] = ok ? ld4(a.G2 + ((size_t)k * a.n_j + r) * kD2 + 4 * lc) : zero4();
         }
-        fence_async_smem();
-        fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            fence_after();
-#pragma unroll
-            for (int kb = 0; kb < 4; ++kb) {
-                const uint64_t ad = umma_desc(smem_u32(As + kb * 16384)), bd = umma_desc(smem_u32(Bs + kb * 8192));
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) mma_tf32(tmem, ad + 2 * ks, bd + 2 * ks, kIdesc, (t != t_begin) || (kb | ks) != 0);
-            }
-            mma_commit(&mma_done);
-        }
-        pending = true;
-    }
-    if (pending) {
-        mbar_wait(&mma_done, parity);
-        fence_after();
-    }
-    {
+    };
+    // read the finished unit back: rows m (hi) + rows 64 + m (lo), columns n (hi) + 32 + n (lo)
+    auto unit_epilogue = [&](int k, int chunk) {
         float v0[32], v1[32];
         const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
         tmem_ld32(taddr, v0);
@@ -348,7 +325,6 @@ __global__ void __launch_bounds__(kThreads, 2) dw2_tc_kernel(const DenseArgs a, 
         fence_before();
         __syncthreads();
         if (warp < 2 && tid < D1) {
-            const float sc = a.mask != nullptr ? a.scale : 1.f;
             float *dst = a.dW2 + ((size_t)k * n_chunks + chunk) * D1 * kD2 + tid * kD2;
 #pragma unroll
             for (int c = 0; c < 8; ++c)
@@ -356,8 +332,78 @@ __global__ void __launch_bounds__(kThreads, 2) dw2_tc_kernel(const DenseArgs a, 
                     (v0[4 * c] + stage[tid * 33 + 4 * c]) * sc, (v0[4 * c + 1] + stage[tid * 33 + 4 * c + 1]) * sc,
                     (v0[4 * c + 2] + stage[tid * 33 + 4 * c + 2]) * sc, (v0[4 * c + 3] + stage[tid * 33 + 4 * c + 3]) * sc);
         }
+        __syncthreads();  // the staging buffer and TMEM are free again
+        fence_after();
+    };
+
+    int u = u_begin;
+    int k = 0, chunk = 0, t = 0, t_end = 0;
+    auto open_unit = [&]() {
+        k = u / n_chunks, chunk = u % n_chunks;
+        t = (int)((long long)chunk * n_tiles / n_chunks), t_end = (int)((long long)(chunk + 1) * n_tiles / n_chunks);
+    };
+    if (u < u_end) {
+        open_unit();
+        fetch(k, t);
     }
-    __syncthreads();
+    uint32_t parity = 0;
+    bool pending = false, prev_closed = false, first = true;
+    int prev_k = 0, prev_chunk = 0;
+    while (u < u_end) {
+        if (pending) {  // the previous tile's MMAs still read the operand tiles
+            mbar_wait(&mma_done, parity);
+            parity ^= 1;
+            fence_after();
+            if (prev_closed) unit_epilogue(prev_k, prev_chunk);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int kblk = 2 * i + (lrow >> 3);  // (lrow + 16 i) >> 3
+#pragma unroll
+            for (int p = 0; p < KB; ++p) {
+                float4 v, hi, lo;
+                v.x = sel(mk[p][i], 4 * lc + 0, h[p][i].x), v.y = sel(mk[p][i], 4 * lc + 1, h[p][i].y);
+                v.z = sel(mk[p][i], 4 * lc + 2, h[p][i].z), v.w = sel(mk[p][i], 4 * lc + 3, h[p][i].w);
+                split4(v, hi, lo);
+                unsigned char *atom = As + kblk * 4096 + p * 1024 + toff;
+                st128(atom, hi);
+                st128(atom + 2048, lo);
+            }
+            float4 hi, lo;
+            split4(gv[i], hi, lo);
+            unsigned char *atom = Bs + kblk * 2048 + toff;
+            st128(atom, hi);
+            st128(atom + 1024, lo);
+        }
+        const bool first_tile = first;
+        // advance to the next tile and start its loads before the MMAs of this one are issued
+        prev_k = k, prev_chunk = chunk, prev_closed = (t + 1 == t_end);
+        first = false;
+        if (++t == t_end) {
+            ++u;
+            first = true;
+            if (u < u_end) open_unit();
+        }
+        if (u < u_end) fetch(k, t);
+        fence_async_smem();
+        fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 16; ++ks) {
+                const uint64_t ad = umma_desc_mn(smem_u32(As + ks * 4096), 1024), bd = umma_desc_mn(smem_u32(Bs + ks * 2048), 1024);
+                mma_tf32(tmem, ad, bd, kIdesc, !first_tile || ks != 0);
+            }
+            mma_commit(&mma_done);
+        }
+        pending = true;
+    }
+    if (pending) {
+        mbar_wait(&mma_done, parity);
+        fence_after();
+        unit_epilogue(prev_k, prev_chunk);
+    }
     if (warp == 0) tmem_dealloc<64>(tmem);
 }
 
@@ -400,17 +446,19 @@ void launch_dh_tc(const DenseArgs &a, int D1, cudaStream_t s) {
     CUDA_CHECK(cudaGetLastError());
 }
 
-// a.n_rb = chunks of row tiles per relation (partials [K][n_rb][D1 * 32], n_rb == 1: the gradient itself)
+// a.n_rb = chunks of row tiles per relation (partials [K][n_rb][D1 * 32], n_rb == 1: the gradient itself);
+// a.n_slots = persistent CTAs
 void launch_dw2_tc(const DenseArgs &a, int D1, cudaStream_t s) {
     if (a.K == 0 || a.n_j == 0) return;
     const size_t bytes = 65536 + 32768 + 64 * 33 * sizeof(float);
     const int n_tiles = dense_tc_tiles(a.n_j);
+    const int grid = std::max(1, std::min(a.K * a.n_rb, a.n_slots));
     if (D1 == 64) {
         set_smem(dw2_tc_kernel<64>, bytes);
-        dw2_tc_kernel<64><<<a.K * a.n_rb, kThreads, bytes, s>>>(a, n_tiles);
+        dw2_tc_kernel<64><<<grid, kThreads, bytes, s>>>(a, n_tiles);
     } else {
         set_smem(dw2_tc_kernel<32>, bytes);
-        dw2_tc_kernel<32><<<a.K * a.n_rb, kThreads, bytes, s>>>(a, n_tiles);
+        dw2_tc_kernel<32><<<grid, kThreads, bytes, s>>>(a, n_tiles);
     }
     CUDA_CHECK(cudaGetLastError());
 }

@@ -22,11 +22,20 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
     return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46) | (2ull << 61);
 }
-// MN-major operand (cute: Swizzle<3,4,3> o ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO))): an atom is 8 K-rows of 128 bytes, a row
-// = 32 consecutive M / N indices at one K; the 16-byte chunk index is XORed with the row index inside the atom
-// exactly as in the K-major tile.  LBO = bytes between atoms along M / N, SBO = bytes between atoms along K; one
-// k-step of 8 tf32 is exactly one atom row group, so successive k-steps use successive descriptors.
-__device__ __forceinline__ uint32_t mn_off(int k_row, int chunk) { return (uint32_t)((k_row & 7) * 128 + ((chunk ^ (k_row & 7)) << 4)); }
+// MN-major tf32 operand: layout type SWIZZLE_128B_BASE32B = 1 (plain SWIZZLE_128B reads as zeros for transposed
+// 32-bit operands; measured with tools/umma_probe.cu on a B200).  An atom is 4 K-rows of 128 bytes, a row = 32
+// consecutive M / N indices at one K; the 32-byte chunk index is XORed with the row index inside the atom
+// (cute: Swizzle<2,5,2> o ((T,8,m),(4,k)):((1,T,LBO),(4T,SBO))).  Measured address map:
+//   byte(mn, k) = (mn >> 5) LBO + (k >> 2) SBO + (k & 3) 128 + ((((mn & 31) >> 3) ^ (k & 3)) << 5) + (mn & 7) 4
+// With SBO = 512 one k-step (8 K-rows) of one 32-wide M / N block is 1024 contiguous bytes.
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes = 512) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46) | (1ull << 61);
+}
+// byte offset of 16-byte chunk `chunk` (4 tf32) of K-row `k_row` inside its 1024-byte k-step block (SBO = 512)
+__device__ __forceinline__ uint32_t mn_off(int k_row, int chunk) {
+    return (uint32_t)(((k_row >> 2) & 1) * 512 + (k_row & 3) * 128 + ((((chunk >> 1) ^ (k_row & 3))) << 5) + (chunk & 1) * 16);
+}
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 at [4,6)), A = B = TF32 (2 at [7,10), [10,13)),
 // A / B major at bits 15 / 16 (0 = K-major, 1 = MN-major), N >> 3 at [17,23), M >> 4 at [24,29)

@@ -314,6 +314,16 @@ class Engine(object):
         check(self.lib.dgn_timing_get(self._h, name.encode(), ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
 
+    def timeline(self):
+        """[(name, lane, start_ms, stop_ms)] of the phases recorded since ``timing_reset``."""
+        out, buf = [], ctypes.create_string_buffer(96)
+        lane, a, b = ctypes.c_int(0), ctypes.c_double(0), ctypes.c_double(0)
+        i = 0
+        while self.lib.dgn_timeline_get(self._h, i, buf, 96, ctypes.byref(lane), ctypes.byref(a), ctypes.byref(b)) == 0:
+            out.append((buf.value.decode(), lane.value, a.value, b.value))
+            i += 1
+        return out
+
     def launch_count(self):
         n = ctypes.c_int64(0)
         check(self.lib.dgn_launch_count(self._h, ctypes.byref(n)))

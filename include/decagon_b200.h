@@ -206,6 +206,10 @@ int dgn_timing_enable(dgn_graph *g, int enable);
 int dgn_timing_reset(dgn_graph *g);
 int dgn_timing_get(dgn_graph *g, const char *name, double *ms_out, int64_t *count_out);
 int dgn_launch_count(dgn_graph *g, int64_t *launches_out);
+/* recorded phase `index` (0 .. until DGN_ERR_INVALID): name, stream lane, start / stop in ms after the first
+ * recorded phase began -- a timeline of one step across the two lanes (tools/timeline.py) */
+int dgn_timeline_get(dgn_graph *g, int index, char *name_out, int name_cap, int *lane_out, double *start_ms_out,
+                     double *stop_ms_out);
 /* CUDA events on the library's stream around a whole region (bench.py times K steps with it) */
 int dgn_timer_start(dgn_graph *g);
 int dgn_timer_stop(dgn_graph *g, double *ms_out);
