@@ -299,6 +299,9 @@ int *upload_wstart(const TaskCsr &t, const SlotTable &slots) {
 struct NodeType {
     int n = 0, F = 0;
     bool feat_set = false, identity = false;
+    HostCsr feat;                // general sparse features (canonical CSR), empty for the identity
+    DevCsr X, Xt;                // device: by node row / by feature
+    int *Xt_eid = nullptr;       // entry of Xt -> its position in X
     std::vector<int> row_groups, col_groups;
     float *H = nullptr, *Z = nullptr, *dZ = nullptr, *dA = nullptr;
     long long *dZq = nullptr;  // dZ accumulated by the decode kernel in fixed point
@@ -348,6 +351,9 @@ struct Group {
     uint32_t *mask1 = nullptr, *mask2 = nullptr;
     long long mask1_words = 0, mask2_words = 0;
     bool dense_tc = false;  // layer-2 contractions on tcgen05 (dense_tc.cu)
+    bool gen_feat = false;  // column type has general sparse features: layer 1 runs on P1 = X W1_k / G1 = A_k^T dS1
+    float *P1buf = nullptr, *G1buf = nullptr;  // [P1][K * n_j][32]
+    long long feat_nnz = 0;
     int n_rb = 1, n_rb_pd = 1, slots_proj = 1, slots_dh = 1, slots_dw2 = 1;  // dense layer-2 kernels: row blocks, CTAs per block
     std::vector<uint32_t *> thr;  // per relation
     std::vector<int> thr_n;
@@ -486,7 +492,7 @@ void free_group_device(Group &G) {
     dev_free(G.wstart_bwd);
     G.slots1 = SlotTable(), G.slots2 = SlotTable(), G.slots_bwd = SlotTable();
     dev_free(G.rel_ids);
-    float **bufs[] = {&G.part1, &G.part2, &G.Y1, &G.n1, &G.Y2, &G.n2, &G.P2, &G.dS, &G.G2, &G.bwd_partial, &G.dW2part, &G.dHpart};
+    float **bufs[] = {&G.part1, &G.part2, &G.Y1, &G.n1, &G.Y2, &G.n2, &G.P2, &G.dS, &G.G2, &G.bwd_partial, &G.dW2part, &G.dHpart, &G.P1buf, &G.G1buf};
     for (float **b : bufs) dev_free(*b);
     dev_free(G.mask1);
     dev_free(G.mask2);
@@ -549,7 +555,9 @@ void build_group(dgn_graph *g, Group &G) {
     HostCsr bwd;
     csr_transpose(fwd, bwd);
 
-    G.staged = g->allow_staged && staged_supported(n_i, n_j, G.K) && G.F_j == n_j;  // by the group-wide K: every rank agrees
+    G.gen_feat = !g->types[G.j].identity;
+    G.feat_nnz = G.gen_feat ? g->types[G.j].feat.nnz() : G.F_j;
+    G.staged = g->allow_staged && staged_supported(n_i, n_j, G.K);  // by the group-wide K: every rank agrees
     const long long target_warps = (long long)g->n_sm * 64 * 2;
     // one quarter-warp per segment: aim at ~2 waves of quarter-warps, 32..2048 non-zeros each
     int seg_len = (int)std::min<long long>(2048, std::max<long long>(32, (G.nnz / (4 * target_warps) + 31) / 32 * 32));
@@ -600,7 +608,11 @@ void build_group(dgn_graph *g, Group &G) {
     G.dS = dev_alloc<float>(panel_floats(P1, n_i));
     G.P2 = dev_alloc<float>(panel_floats(1, (long long)K * n_j));
     G.G2 = dev_alloc<float>(panel_floats(1, (long long)K * n_j));
-    G.mask1_words = ((long long)K * G.F_j + 31) / 32;
+    G.mask1_words = ((long long)K * G.feat_nnz + 31) / 32;  // identity features: one bit per row of W1_k
+    if (G.gen_feat) {
+        G.P1buf = dev_alloc<float>(panel_floats(P1, (long long)K * n_j));
+        G.G1buf = dev_alloc<float>(panel_floats(P1, (long long)K * n_j));
+    }
     G.mask2_words = (long long)K * n_j * P1;
     G.mask1 = dev_alloc<uint32_t>((size_t)G.mask1_words);
     G.mask2 = dev_alloc<uint32_t>((size_t)G.mask2_words);
@@ -726,7 +738,7 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step, StepDep
         for (auto &G : g->groups) {
             PhaseScope ph(g, "mask", -1, G.lane);
             cudaStream_t s = lane_stream(g, G.lane);
-            launch_gen_mask(G.mask1, G.mask1_words, G.F_j, 0, G.rel_ids, kStreamDropout1, step, seed, thr, s);
+            launch_gen_mask(G.mask1, G.mask1_words, G.feat_nnz, 0, G.rel_ids, kStreamDropout1, step, seed, thr, s);
             g->launches++;
             launch_gen_mask(G.mask2, G.mask2_words, (long long)G.n_j * g->d1, G.n_j * P1, G.rel_ids, kStreamDropout2, step, seed, thr, s);
             g->launches++;
@@ -798,7 +810,18 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step, StepDep
         Group &G = g->groups[gi];
         {
             PhaseScope ph(g, "spmm_fwd1", gi, G.lane);
-            spmm_fwd(G, g->params + G.w1_off, P1, (long long)G.Kl * G.F_j, G.part1, G.slots1, G.wstart1, drop ? G.mask1 : nullptr);
+            if (G.gen_feat) {  // P1_k = (X_j (.) m_k / q) W1_k, then the SpMM on P1 like layer 2 on P2
+                NodeType &Tj = g->types[G.j];
+                FeatArgs f = {};
+                f.rowptr = Tj.X.rowptr, f.col = Tj.X.col, f.val = Tj.X.val, f.eid = nullptr;
+                f.n_rows = G.n_j, f.in_rows = G.F_j, f.in = g->params + G.w1_off, f.out = G.P1buf;
+                f.K = G.Kl, f.P = P1, f.nnz = G.feat_nnz, f.mask = drop ? G.mask1 : nullptr, f.scale = scale;
+                launch_feature_product(f, lane_stream(g, G.lane));
+                g->launches++;
+                spmm_fwd(G, G.P1buf, P1, (long long)G.Kl * G.n_j, G.part1, G.slots1, G.wstart1, nullptr);
+            } else {
+                spmm_fwd(G, g->params + G.w1_off, P1, (long long)G.Kl * G.F_j, G.part1, G.slots1, G.wstart1, drop ? G.mask1 : nullptr);
+            }
             if (G.partitioned) exchange(g, G, 0, G.part1, G.slots1.n_slots, lane_stream(g, G.lane));
         }
         produced(g, D.S1[gi], G.lane);
@@ -962,6 +985,17 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam) {
             g->launches++;
         }
         PhaseScope ph(g, "spmm_bwd1", gi, G.lane);
+        if (G.gen_feat) {  // G1_k = A_k^T dS1, then dW1_k = (X_j (.) m_k / q)^T G1_k
+            spmm_bwd(G, P1, G.G1buf, (long long)G.Kl * G.n_j, nullptr, false);
+            NodeType &Tj = g->types[G.j];
+            FeatArgs f = {};
+            f.rowptr = Tj.Xt.rowptr, f.col = Tj.Xt.col, f.val = Tj.Xt.val, f.eid = Tj.Xt_eid;
+            f.n_rows = G.F_j, f.in_rows = G.n_j, f.in = G.G1buf, f.out = g->grads + G.w1_off;
+            f.K = G.Kl, f.P = P1, f.nnz = G.feat_nnz, f.mask = drop ? G.mask1 : nullptr, f.scale = scale;
+            launch_feature_product(f, s);
+            g->launches++;
+            continue;
+        }
         spmm_bwd(G, P1, g->grads + G.w1_off, (long long)G.Kl * G.F_j, drop ? G.mask1 : nullptr, adam.alpha != 0.f && G.tstaged && g->fuse_adam);
     }
     for (auto &d : deferred_dw2) run_dw2(d.first, d.second);
@@ -1307,6 +1341,9 @@ extern "C" int dgn_graph_destroy(dgn_graph *g) {
         dev_free(T.dZ);
         dev_free(T.dZq);
         dev_free(T.dA);
+        free_csr(T.X);
+        free_csr(T.Xt);
+        dev_free(T.Xt_eid);
     }
     free_arena(g);
     free_comm(g);
@@ -1362,11 +1399,9 @@ extern "C" int dgn_graph_set_features(dgn_graph *g, int type, int32_t n_rows, in
         identity = coo_rows[e] == coo_cols[e] && coo_rows[e] >= 0 && coo_rows[e] < n_rows && vals[e] == 1.f && !seen[coo_rows[e]];
         if (identity) seen[coo_rows[e]] = 1;
     }
-    if (!identity)
-        DGN_FAIL(DGN_ERR_UNSUPPORTED,
-                 "features of type %d are not the identity: general sparse features are not implemented yet "
-                 "(SURVEY.md 8f rank 2); every BASELINE config uses identity features", type);
-    T.identity = true;
+    T.identity = identity;
+    T.feat = HostCsr();
+    if (!identity) csr_from_coo(n_rows, n_cols, nnz, coo_rows, coo_cols, vals, T.feat);  // canonical (row, col) order
     T.feat_set = true;
     g->finalized = false;
     DGN_API_END
@@ -1396,12 +1431,30 @@ extern "C" int dgn_graph_finalize(dgn_graph *g) {
     for (auto &G : g->groups) {
         for (int k = 0; k < G.K; ++k) DGN_REQUIRE(G.rel_set[k], "relation (%d,%d,%d) was never set", G.i, G.j, k);
         DGN_REQUIRE(g->types[G.j].feat_set, "features of node type %d were never set", G.j);
-        DGN_REQUIRE(G.F_j == G.n_j, "identity features need feat_dim == n_nodes for type %d", G.j);
+        DGN_REQUIRE(!g->types[G.j].identity || G.F_j == G.n_j, "identity features need feat_dim == n_nodes for type %d", G.j);
     }
     CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    for (auto &T : g->types) {
+        free_csr(T.X);
+        free_csr(T.Xt);
+        dev_free(T.Xt_eid);
+        if (!T.feat_set || T.identity) continue;
+        // X^T by feature, every entry remembering its position in X (= its dropout bit)
+        HostCsr Xt;
+        csr_transpose(T.feat, Xt);
+        std::vector<int> eid(T.feat.col.size());
+        {
+            std::vector<int> cursor(Xt.rowptr.begin(), Xt.rowptr.end() - 1);
+            for (int r = 0; r < T.feat.n_rows; ++r)
+                for (int e = T.feat.rowptr[r]; e < T.feat.rowptr[r + 1]; ++e) eid[cursor[T.feat.col[e]]++] = e;
+        }
+        T.X = upload_csr(T.feat);
+        T.Xt = upload_csr(Xt);
+        T.Xt_eid = dev_upload(eid);
+    }
     for (auto &G : g->groups) {
         // multi-GPU: groups that take the staged path (many small relations) are partitioned by relation
-        G.partitioned = g->world > 1 && g->allow_staged && staged_supported(G.n_i, G.n_j, G.K) && G.F_j == G.n_j && G.K >= 8 * g->world;
+        G.partitioned = g->world > 1 && g->allow_staged && staged_supported(G.n_i, G.n_j, G.K) && G.K >= 8 * g->world;
         std::vector<int> loc;
         if (G.partitioned) {
             std::vector<int64_t> w(G.K);
@@ -1689,7 +1742,7 @@ extern "C" int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t
             }
         };
         for (auto &Gq : g->groups)
-            if (Gq.tstaged && g->fuse_adam && adam.alpha != 0.f) {
+            if (Gq.tstaged && !Gq.gen_feat && g->fuse_adam && adam.alpha != 0.f) {
                 flush(Gq.w1_off);
                 begin = Gq.w1_off + (size_t)Gq.Kl * Gq.F_j * g->d1;
             }

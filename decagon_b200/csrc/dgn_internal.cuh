@@ -186,6 +186,22 @@ struct DenseArgs {
     int n_slots;  // persistent CTAs per row block; slot s owns relations [s K / n_slots, (s+1) K / n_slots)
 };
 
+// first-layer product with general (non-identity) sparse features, features.cu
+struct FeatArgs {
+    const int *rowptr, *col;  // CSR view: X by node row (forward) or X^T by feature (backward)
+    const float *val;
+    const int *eid;           // backward view: position of the entry in X's canonical order; forward: null (= e)
+    int n_rows;               // rows of the view = rows per relation of the output
+    int in_rows;              // rows per relation of the dense input
+    const float *in;          // [P][K * in_rows][32]
+    float *out;               // [P][K * n_rows][32]
+    int K, P;
+    long long nnz;            // non-zeros of X: relation k owns dropout bits [k nnz, (k + 1) nnz)
+    const uint32_t *mask;     // packed keep bits or null
+    float scale;
+};
+void launch_feature_product(const FeatArgs &a, cudaStream_t s);
+
 struct DecodeArgs {
     const float *Zi, *Zj;  // [n][32]
     long long *dZi, *dZj;  // 2^-40 fixed point (order-independent scatter-add)

@@ -28,8 +28,25 @@ GraphInputs = namedtuple('GraphInputs', [
 DEFAULT_DECODERS = {(0, 0): 'bilinear', (0, 1): 'bilinear', (1, 0): 'bilinear', (1, 1): 'dedicom'}
 
 
-def assemble(gene_adj, gene_drug_adj, drug_drug_adj_list, decoders=None, transpose=True):
-    """Raw scipy matrices -> the dicts of the drop-in surface."""
+def multi_hot_features(n_nodes, n_feat, per_row=12, seed=0):
+    """Multi-hot node features shaped like the reference's drug features (one column per mono side effect, a 1
+    for every side effect of the drug, ``DecagonPublicDataNodeFeaturesBuilder.py:34-51``): ``per_row`` distinct
+    columns on average, heavy-tailed column popularity, every row non-empty."""
+    rng = np.random.RandomState(seed)
+    pop = 1.0 / np.sqrt(np.arange(1, n_feat + 1))
+    pop /= pop.sum()
+    rows, cols = [], []
+    for r in range(n_nodes):
+        c = np.unique(rng.choice(n_feat, size=max(1, rng.poisson(per_row)), p=pop))
+        rows.append(np.full(len(c), r))
+        cols.append(c)
+    rows, cols = np.concatenate(rows), np.concatenate(cols)
+    return sp.csr_matrix((np.ones(len(rows)), (rows, cols)), shape=(n_nodes, n_feat))
+
+
+def assemble(gene_adj, gene_drug_adj, drug_drug_adj_list, decoders=None, transpose=True, features=None):
+    """Raw scipy matrices -> the dicts of the drop-in surface.  ``features``: {node type: scipy sparse [n, F]}
+    replaces the identity features of that type (``DecagonDataSet.py:110-131`` builds the same tuples)."""
     adj = {
         (0, 0): [RelationCsrMatrix(gene_adj)],
         (0, 1): [RelationCsrMatrix(gene_drug_adj)],
@@ -49,6 +66,8 @@ def assemble(gene_adj, gene_drug_adj, drug_drug_adj_list, decoders=None, transpo
     n_genes, n_drugs = gene_drug_adj.shape
     feat = {0: preprocessing.sparse_to_tuple(sp.identity(n_genes).tocoo()),
             1: preprocessing.sparse_to_tuple(sp.identity(n_drugs).tocoo())}
+    for t, x in (features or {}).items():
+        feat[t] = preprocessing.sparse_to_tuple(sp.coo_matrix(x))
     num_feat = {t: f[2][1] for t, f in feat.items()}
     nonzero_feat = {t: int(f[1].sum()) for t, f in feat.items()}
 
@@ -64,7 +83,7 @@ def assemble(gene_adj, gene_drug_adj, drug_drug_adj_list, decoders=None, transpo
                        edge_type2dim, dec, {0: n_genes, 1: n_drugs})
 
 
-def toy_graph(decoders=None, seed=0):
+def toy_graph(decoders=None, seed=0, features=None):
     """Config #1.  ``np.random.seed(seed)`` then the draws of ``main.py:134-156``."""
     import networkx as nx
     np.random.seed(seed)
@@ -75,7 +94,7 @@ def toy_graph(decoders=None, seed=0):
     shared = (gene_drug_adj.T @ gene_drug_adj).toarray()
     np.fill_diagonal(shared, -1)
     drug_drug = [sp.csr_matrix((shared == t + 4).astype(np.float64)) for t in range(n_types)]
-    return assemble(gene_adj, gene_drug_adj, drug_drug, decoders)
+    return assemble(gene_adj, gene_drug_adj, drug_drug, decoders, features=features)
 
 
 def _unique_pairs(rng, n, p, count):
@@ -100,7 +119,7 @@ def _symmetric(n, u, v):
 
 def polypharmacy_graph(scale=1, n_types=964, decoders=None, seed=0,
                        n_proteins=19085, n_drugs=645, n_ppi=715612, n_targets=18596,
-                       n_pairs=63473, n_ddi=4651131, min_size=500, max_size=28568):
+                       n_pairs=63473, n_ddi=4651131, min_size=500, max_size=28568, features=None):
     """Config #3 (``scale=1``) / #5 (``scale=10``): node and edge counts scale, the number of
     side-effect types does not."""
     rng = np.random.RandomState(seed)
@@ -133,4 +152,4 @@ def polypharmacy_graph(scale=1, n_types=964, decoders=None, seed=0,
     for c in sizes:
         pick = rng.choice(base, size=int(c), replace=False)
         drug_drug.append(_symmetric(n1, bu[pick], bv[pick]))
-    return assemble(gene_adj, gene_drug_adj, drug_drug, decoders)
+    return assemble(gene_adj, gene_drug_adj, drug_drug, decoders, features=features)

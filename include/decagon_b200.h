@@ -93,7 +93,10 @@ int dgn_graph_set_relation(dgn_graph *g, int r, int32_t n_rows, int32_t n_cols, 
                            const int32_t *coo_cols, const float *vals);
 /* placeholders['feat_%d'] (DecagonDataSet.py:117-118; minibatch.py:264): sparse node features
  * of one type as COO float32.  Identity features (every BASELINE config) take the row-gather
- * fast path. */
+ * fast path (layers.py:89 becomes a masked row gather of W1_k).  Any other matrix (the public data's multi-hot
+ * drug features, DecagonPublicDataNodeFeaturesBuilder.py:34-51) is canonicalised to CSR sorted by (row, col);
+ * layer 1 then runs P1_k = (X (.) m_k / q) W1_k followed by the SpMM on P1_k, dropout bit e of a relation =
+ * non-zero e in that order (dropout_sparse, layers.py:23-31), and dW1_k = (X (.) m_k / q)^T (A_k^T dS1). */
 int dgn_graph_set_features(dgn_graph *g, int type, int32_t n_rows, int32_t n_cols, int64_t nnz,
                            const int32_t *coo_rows, const int32_t *coo_cols, const float *vals);
 /* DecagonOptimizer's per-relation unigram tables (optimizer.py:36-47): degrees[i][k] of the

@@ -16,11 +16,12 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)) if b.size else 0.0
 
 
-def mini_poly(n_types=12, seed=0):
+def mini_poly(n_types=12, seed=0, features=None):
     """A small graph with the structure of config #3 (many small drug-drug relations), big
     enough to take the staged SpMM path (K >= 8)."""
     return datasets.polypharmacy_graph(n_types=n_types, seed=seed, n_proteins=300, n_drugs=97, n_ppi=2500,
-                                       n_targets=400, n_pairs=1500, n_ddi=9000, min_size=100, max_size=1400)
+                                       n_targets=400, n_pairs=1500, n_ddi=9000, min_size=100, max_size=1400,
+                                       features=features)
 
 
 class Case(object):

@@ -278,3 +278,37 @@ def test_dense_layer2_tensor_cores_match_cuda_cores(h1):
             assert rel_err(tcore.embeddings(t), ffma.embeddings(t)) <= TOL
     ffma.close()
     tcore.close()
+
+
+@pytest.mark.parametrize('graph_kind', ['toy', 'mini'])
+def test_general_sparse_features(graph_kind):
+    """Non-identity node features (the reference's public data gives drugs multi-hot side-effect
+    features, DecagonPublicDataNodeFeaturesBuilder.py:34-51): layer 1 is X_j W1_k with dropout on the feature
+    non-zeros (layers.py:23-31, 89).  Forward, every gradient and an Adam step against the float64 oracle, on
+    the gather path (toy) and on the staged path (mini: many small relations)."""
+    if graph_kind == 'toy':
+        feats = {1: datasets.multi_hot_features(400, 150, per_row=6, seed=3)}
+        c = Case(datasets.toy_graph(features=feats))
+    else:
+        feats = {1: datasets.multi_hot_features(97, 213, per_row=9, seed=4),
+                 0: datasets.multi_hot_features(300, 64, per_row=3, seed=5)}
+        c = Case(common.mini_poly(n_types=10, seed=9, features=feats), batch_size=64)
+    assert c.inputs.num_feat[1] == feats[1].shape[1] and c.inputs.nonzero_feat[1] == feats[1].nnz
+    eng = c.engine()
+    assert eng.get_param(_lib.PARAM_W1, (1, 1), 0).shape == (feats[1].shape[1], 64)
+    for rate in (0.0, 0.1):
+        check_forward(c, eng, rate, 2)
+        for step, (r, batch) in enumerate(c.batches(4)):
+            check_grads(c, eng, r, batch, rate, step, 'hinge')
+    # optimizer steps (no fused Adam on this path): TF-1.8 ApplyAdam applied to the gradients the device produced
+    eng.reset_optimizer()
+    p = O.cast_params(eng.get_params(), np.float32)
+    adam = O.AdamTF1(p, lr=1e-3)
+    for step, (r, batch) in enumerate(c.batches(3)):
+        eng.train_step(r, batch, negatives=None, seed=SEED, step=step, dropout=0.1, apply_update=True)
+        adam.apply(p, eng.get_grads())
+        now = eng.get_params()
+        for name in p:
+            for gg in p[name]:
+                assert np.abs(now[name][gg] - p[name][gg]).max() <= 2e-7, (step, name, gg)
+    eng.close()
