@@ -244,3 +244,77 @@ def test_device_auc_with_ties_and_empty_classes():
     with pytest.raises(ValueError):
         eng.evaluate_edges((1, 1), [99], [[0, 0]], [1])
     eng.close()
+
+
+def test_ndarray_dumps_and_variable_checkpoints(tmp_path):
+    """The reference's on-disk formats (CheckpointToNdarrayWriter.py:105-169, DecagonLogger.py:232-287) and what
+    NpPredictor._predictEdges (NpPredictor.py:304-319) computes from them; variables under their TF names."""
+    from decagon_b200 import ndarray_io
+    from decagon_b200.evaluator import sigmoid
+    inputs = datasets.toy_graph()
+    placeholders, minibatch, model, opt = build_trainable(inputs)
+    sess = tf.Session(seed=SEED)
+    sess.run(tf.global_variables_initializer())
+    np.random.seed(1)
+    minibatch.shuffle()
+    for _ in range(5):
+        fd = minibatch.update_feed_dict(minibatch.next_minibatch_feed_dict(placeholders), 0.1, placeholders)
+        sess.run([opt.opt_op, opt.cost, opt.batch_edge_type_idx], feed_dict=fd)
+
+    ids = ['C0000%d' % k for k in range(3)]  # 3 side effects + their transposed twins = 6 relations of (1, 1)
+    out = str(tmp_path / 'np') + '/'
+    files = ndarray_io.write_ndarrays(sess, model, minibatch, out, side_effect_ids=ids)  # dropout 0 feed, as the writer builds it
+    names = sorted(f.rsplit('/', 1)[1] for f in files)
+    assert names == sorted(['embeddings.npy', 'GlobalRelations.npy'] + ['EmbeddingImportance-%s.npy' % i for i in ids]
+                           + ['EmbeddingImportance-%s-Transposed.npy' % i for i in ids])
+    emb, imp, glb = ndarray_io.read_ndarrays(out, ids[1])
+    assert emb.shape == (400, 32) and emb.dtype == np.float32 and imp.shape == glb.shape == (32, 32)
+
+    # NpPredictor on the files == the session's predictions for relation (1, 1, 1)
+    rel = (1, 1, 1)
+    feed = dict(fd)
+    feed[placeholders['dropout']] = 0
+    feed[placeholders['batch_edge_type_idx']] = minibatch.edge_type2idx[rel]
+    feed[placeholders['batch_row_edge_type']], feed[placeholders['batch_col_edge_type']] = 1, 1
+    pred = sigmoid(sess.run(opt.predictions, feed_dict=feed))
+    edges = np.random.RandomState(0).randint(0, 400, (500, 2))
+    want = np.take(pred, edges[:, 0] * 400 + edges[:, 1])
+    assert rel_err(ndarray_io.np_predict_edges(emb, imp, glb, edges), want) <= 1e-5
+
+    # the logger's single-archive variant
+    ndarray_io.write_ndarrays(sess, model, minibatch, out, logger_format=True)
+    stacked = np.load(out + 'EmbeddingImportance.npyz.npz')['arr_0']
+    assert stacked.shape == (6, 32, 32) and np.array_equal(stacked[1], imp)
+
+    # the files loaded into a bare engine reproduce the same probabilities on the device
+    case = common.Case(inputs)
+    eng = case.engine()
+    eng.forward(0.0, 0, 0)
+    ndarray_io.load_dedicom(eng, out, ids + [i + '-Transposed' for i in ids])
+    got = eng.predict_edges(case.it.edge_type2idx[rel], edges, sigmoid=True)
+    assert rel_err(got, want) <= 1e-5
+    eng.close()
+
+    # variables under their TF graph names: save, load into a second model, same embeddings and scores
+    ckpt = str(tmp_path / 'variables.npz')
+    saved = ndarray_io.save_variables(sess, model, ckpt)
+    assert len(saved) == len(model.vars) and all(n in model.vars for n in saved)
+    placeholders2, minibatch2, model2, opt2 = build_trainable(inputs)
+    sess2 = tf.Session(seed=SEED + 1)
+    sess2.run(tf.global_variables_initializer())
+    feed2 = minibatch2.update_feed_dict(minibatch2.next_minibatch_feed_dict(placeholders2), 0.0, placeholders2)
+    feed2[placeholders2['batch_edge_type_idx']] = minibatch2.edge_type2idx[rel]
+    feed2[placeholders2['batch_row_edge_type']], feed2[placeholders2['batch_col_edge_type']] = 1, 1
+    before = sess2.run(opt2.predictions, feed_dict=feed2)
+    # the second model was built under fresh name scopes: map by position through the shared naming scheme
+    data = dict(np.load(ckpt))
+    renamed = {v2.name: data[v1.name] for v1, v2 in zip(model._variables(), model2._variables())}
+    np.savez(str(tmp_path / 'renamed.npz'), **renamed)
+    loaded = ndarray_io.load_variables(sess2, model2, str(tmp_path / 'renamed.npz'))
+    assert len(loaded) == len(saved)
+    after = sigmoid(sess2.run(opt2.predictions, feed_dict=feed2))
+    assert rel_err(after, pred) <= 1e-6 and rel_err(sigmoid(before), pred) > 1e-3
+    np.savez(str(tmp_path / 'partial.npz'), **{k: v for k, v in list(renamed.items())[:3]})
+    with pytest.raises(KeyError):
+        ndarray_io.load_variables(sess2, model2, str(tmp_path / 'partial.npz'))
+    assert len(ndarray_io.load_variables(sess2, model2, str(tmp_path / 'partial.npz'), strict=False)) == 3

@@ -289,3 +289,15 @@ def test_relation_matrix_types():
     t = m.transpose(copy=True, setId=True)
     assert m.isTranspose and t.isTranspose and m.transposedMtxLink is t and t.transposedMtxLink is m
     assert m.id != t.id and m.tocoo().id == m.id and m.tocoo().tocsr().transposedMtxLink is t
+
+
+def test_ndarray_io_predict_matches_nppredictor_golden():
+    """ndarray_io.np_predict_edges restates NpPredictor._predictEdges (NpPredictor.py:304-319): same numbers as the
+    reference's own source run on its dumped R / D_k (tests/golden/nppredictor.npz)."""
+    from decagon_b200 import ndarray_io
+    gold = np.load(os.path.join(GOLDEN, 'nppredictor.npz'))
+    R, D, Z, edges = gold['R'], gold['D'], gold['Z'], gold['edges']
+    for k in range(D.shape[0]):
+        want = gold['pred%d' % k]
+        got = ndarray_io.np_predict_edges(Z, D[k], R, edges)
+        assert np.abs(got - want[:, 2]).max() <= 2e-6
