@@ -7,71 +7,37 @@
 //     a b ~= a_hi b_hi + a_lo b_hi + a_hi b_lo,   x_hi = x with the 13 low mantissa bits cleared, x_lo = x - x_hi
 // (kind::tf32 ignores those 13 bits, so hi is exact and lo carries the next 11 bits: error ~2^-22).
 //
-// CTA = (column tile of 128 nodes of Z_j, worker), two CTAs per SM; a worker loops over relations.  Per relation
-// the threads form B_r = Z_j M_r^T for the CTA's 128 columns on the CUDA cores (thread = column node, its
-// Z_j row lives in registers for the whole kernel), split it and write hi / lo as K-major SWIZZLE_128B
-// operand tiles into shared memory.  Per 128-row tile of Z_i the rows are split and written the same
-// way, one elected thread issues the 12 tcgen05.mma (3 passes x 4 k-steps of 8) that accumulate the
-// [128, 128] fp32 tile in tensor memory, tcgen05.commit signals an mbarrier, and the 4 warps read the
-// accumulator back with tcgen05.ld (32 lanes x 32 columns per instruction), transpose 32 x 32 blocks
-// through shared memory and store full 128-byte row pieces.  The kernel is bound by the output write
-// (1.66 MB per relation); the tensor pipe is busy for a few per cent of the time by construction.
+// CTA = (column tile of NT <= 224 nodes of Z_j, worker), 256 threads, two CTAs per SM; a worker loops over relations.
+// NT is the node count split evenly into tiles of at most 224 columns and rounded up to 16 (645 -> 3 x 224), so the
+// padding of the last tile stays at a few per cent.  Per relation the threads form B_r = Z_j M_r^T for the CTA's
+// columns on the CUDA cores (thread = column node, its Z_j row lives in registers for the whole kernel), split it
+// and write hi / lo as K-major SWIZZLE_128B operand tiles.  Per 128-row tile of Z_i the rows are split and written
+// the same way, one elected thread issues the 12 tcgen05.mma (3 passes x 4 k-steps of 8, N = NT) that accumulate
+// the [128, NT] fp32 tile in tensor memory, tcgen05.commit signals an mbarrier, and the 8 warps read the accumulator
+// back (tcgen05.ld, 32 lanes x 32 columns; the two warps of a lane quarter take alternate column chunks), transpose
+// 32 x 32 blocks through shared memory (STS.128 into rows of 36 floats, LDS.32 along columns) and store 128-byte
+// row pieces; full row tiles take a path without per-row bounds checks.  The kernel is bound by the output
+// write (1.66 MB per relation) and by the instruction count of that read-back.
 #include <algorithm>
 
 #include "dgn_internal.cuh"
+#include "tc_common.cuh"
 
 namespace dgn {
 namespace {
 
 constexpr int D = 32;            // hidden2 = K of the GEMM
 constexpr int kTileM = 128;      // rows of Z_i per MMA
-constexpr int kTileN = 128;      // columns (nodes of Z_j) per CTA = threads; two CTAs per SM overlap their phases
-constexpr int kThreads = 128;
-constexpr uint32_t kTmemCols = 128;
+constexpr int kMaxN = 224;       // columns (nodes of Z_j) per CTA at most
+constexpr int kThreads = 256;
+constexpr uint32_t kTmemCols = 256;
+constexpr int kStageStride = 36;                       // floats per staged row: STS.128 / LDS.32 both conflict-free
+constexpr int kStageBytes = 32 * kStageStride * 4;     // per warp
+constexpr int kSmemB = kMaxN * 128;                    // one B tile (hi or lo)
+constexpr int kSmemBytes = 2 * kSmemB + 8 * kStageBytes;  // B hi, B lo, then A hi / A lo overlaid by the 8 staging blocks
+static_assert(8 * kStageBytes >= 2 * 16384, "the staging blocks cover the A tiles");
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// byte offset of the 16-byte chunk `chunk` (4 floats) of row `row` in a K-major SWIZZLE_128B tile whose rows
-// are 128 bytes (= 32 tf32 = the whole K): 8-row groups of 1024 bytes, chunk index XOR row-in-group
-__device__ __forceinline__ uint32_t sw128(int row, int chunk) {
-    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
-}
-
-// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in [0,14), leading byte
-// offset >> 4 in [16,30) (unused for swizzled K-major: 1), stride byte offset >> 4 in [32,46) (1024 B between
-// 8-row groups), version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3fff) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 at [4,6)), A = B = TF32 (2 at [7,10), [10,13)),
-// both K-major (0 at bits 15, 16), N >> 3 at [17,23), M >> 4 at [24,29)
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t done = 0;
-    for (long long spin = 0; !done; ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-        if (spin > (1ll << 26)) __trap();  // a lost MMA must fault, not hang the device
-    }
-}
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+using namespace tc;
 
 __device__ __forceinline__ float relation_entry(int decoder, const float *glb, const float *loc, int p, int q) {
     switch (decoder) {
@@ -82,48 +48,41 @@ __device__ __forceinline__ float relation_entry(int decoder, const float *glb, c
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 2) predict_tc_kernel(const PredictArgs a, int n_workers) {
+__global__ void __launch_bounds__(kThreads, 2) predict_tc_kernel(const PredictArgs a, int n_workers, int NT) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char *Bhi = smem;                         // [128 rows][128 B]
-    unsigned char *Blo = smem + 16384;
-    unsigned char *Ahi = smem + 32768;                 // [128 rows][128 B]
-    unsigned char *Alo = smem + 49152;
-    float *stage = reinterpret_cast<float *>(smem + 65536);  // [4 warps][32][33]
+    unsigned char *Bhi = smem, *Blo = smem + kSmemB;
+    unsigned char *Ahi = smem + 2 * kSmemB, *Alo = Ahi + 16384;
     __shared__ __align__(16) float Ms[D][D];
     __shared__ __align__(8) uint64_t mma_done;
     __shared__ uint32_t tmem_base_slot;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nt = blockIdx.x / n_workers, worker = blockIdx.x % n_workers;
-    const int v0 = nt * kTileN;
+    const int v0 = nt * NT;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "n"(kTmemCols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    if (tid == 0) {
-        mbar_init(&mma_done, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (warp == 0) tmem_alloc<kTmemCols>(&tmem_base_slot);
+    if (tid == 0) mbar_init(&mma_done, 1);
+    fence_before();
     __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    fence_after();
     const uint32_t tmem = tmem_base_slot;
     if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B operand tiles need 1024-byte alignment
 
-    // this thread's column node: its embedding stays in registers
-    float zj[D];
-    {
-        const int v = v0 + tid;
-#pragma unroll
-        for (int q = 0; q < D; q += 4) {
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (v < a.n_j) x = *reinterpret_cast<const float4 *>(a.Zj + (size_t)v * D + q);
-            zj[q] = x.x, zj[q + 1] = x.y, zj[q + 2] = x.z, zj[q + 3] = x.w;
-        }
-    }
     const int n_mt = (a.n_i + kTileM - 1) / kTileM;
+    const int n_chunks = (NT + 31) >> 5;
+    const int quarter = warp & 3, half = warp >> 2;
+    float *st = reinterpret_cast<float *>(Ahi + warp * kStageBytes);
     uint32_t parity = 0;
+    const int arow = tid & 127, ac0 = (tid >> 7) * 4;
+    float4 ax[4];
+    auto load_a = [&](int mt) {
+        const int u = mt * kTileM + arow;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            ax[c] = u < a.n_i ? __ldg(reinterpret_cast<const float4 *>(a.Zi + (size_t)u * D + 4 * (ac0 + c))) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    load_a(0);
 
     for (int k = worker; k < a.count; k += n_workers) {
         const float *loc = a.loc != nullptr ? a.loc + (size_t)k * a.loc_stride : nullptr;
@@ -131,7 +90,19 @@ __global__ void __launch_bounds__(kThreads, 2) predict_tc_kernel(const PredictAr
         for (int i = tid; i < D * D; i += kThreads) Ms[i >> 5][i & 31] = relation_entry(a.decoder, a.glb, loc, i >> 5, i & 31);
         __syncthreads();
         // B_r[v][p] = sum_q M[p][q] Z_j[v][q]
-        {
+        if (tid < NT) {
+            // this thread's column node (re-read per relation from L2: keeping it would cost 32 registers that
+            // the read-back loop needs for its loads in flight)
+            float zj[D];
+            {
+                const int v = v0 + tid;
+#pragma unroll
+                for (int q = 0; q < D; q += 4) {
+                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (v < a.n_j) x = __ldg(reinterpret_cast<const float4 *>(a.Zj + (size_t)v * D + q));
+                    zj[q] = x.x, zj[q + 1] = x.y, zj[q + 2] = x.z, zj[q + 3] = x.w;
+                }
+            }
             float b[D];
 #pragma unroll
             for (int p = 0; p < D; ++p) {
@@ -146,102 +117,95 @@ __global__ void __launch_bounds__(kThreads, 2) predict_tc_kernel(const PredictAr
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 float4 hi, lo;
-                hi.x = tf32_hi(b[4 * c]), hi.y = tf32_hi(b[4 * c + 1]), hi.z = tf32_hi(b[4 * c + 2]), hi.w = tf32_hi(b[4 * c + 3]);
-                lo.x = b[4 * c] - hi.x, lo.y = b[4 * c + 1] - hi.y, lo.z = b[4 * c + 2] - hi.z, lo.w = b[4 * c + 3] - hi.w;
+                split4(make_float4(b[4 * c], b[4 * c + 1], b[4 * c + 2], b[4 * c + 3]), hi, lo);
                 const uint32_t off = sw128(tid, c);
-                *reinterpret_cast<float4 *>(Bhi + off) = hi;
-                *reinterpret_cast<float4 *>(Blo + off) = lo;
+                st128(Bhi + off, hi);
+                st128(Blo + off, lo);
             }
         }
         float *out = a.out + (size_t)k * a.n_i * a.n_j;
         for (int mt = 0; mt < n_mt; ++mt) {
             const int u0 = mt * kTileM;
-            // A tile: rows u0 .. u0 + 127 of Z_i, split; thread = row
+            // A tile: rows u0 .. u0 + 127 of Z_i, split; thread = (row, half of the row's 8 chunks); the rows were
+            // loaded one tile ahead
             {
-                const int row = tid;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (u0 + row < a.n_i) x = *reinterpret_cast<const float4 *>(a.Zi + (size_t)(u0 + row) * D + 4 * c);
+                for (int c = 0; c < 4; ++c) {
                     float4 hi, lo;
-                    hi.x = tf32_hi(x.x), hi.y = tf32_hi(x.y), hi.z = tf32_hi(x.z), hi.w = tf32_hi(x.w);
-                    lo.x = x.x - hi.x, lo.y = x.y - hi.y, lo.z = x.z - hi.z, lo.w = x.w - hi.w;
-                    const uint32_t off = sw128(row, c);
-                    *reinterpret_cast<float4 *>(Ahi + off) = hi;
-                    *reinterpret_cast<float4 *>(Alo + off) = lo;
+                    split4(ax[c], hi, lo);
+                    const uint32_t off = sw128(arow, ac0 + c);
+                    st128(Ahi + off, hi);
+                    st128(Alo + off, lo);
                 }
+                load_a(mt + 1 < n_mt ? mt + 1 : 0);
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            fence_async_smem();
+            fence_before();
             __syncthreads();
             if (tid == 0) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                fence_after();
                 const uint64_t ahi = umma_desc(smem_u32(Ahi)), alo = umma_desc(smem_u32(Alo));
                 const uint64_t bhi = umma_desc(smem_u32(Bhi)), blo = umma_desc(smem_u32(Blo));
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {  // K = 8 tf32 = 32 bytes per instruction: + 2 in the encoded address
-                    mma_tf32(tmem, ahi + 2 * ks, bhi + 2 * ks, ks > 0);
-                    mma_tf32(tmem, alo + 2 * ks, bhi + 2 * ks, 1);
-                    mma_tf32(tmem, ahi + 2 * ks, blo + 2 * ks, 1);
+                    mma_tf32(tmem, ahi + 2 * ks, bhi + 2 * ks, idesc, ks > 0);
+                    mma_tf32(tmem, alo + 2 * ks, bhi + 2 * ks, idesc, 1);
+                    mma_tf32(tmem, ahi + 2 * ks, blo + 2 * ks, idesc, 1);
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_done)) : "memory");
+                mma_commit(&mma_done);
             }
             mbar_wait(&mma_done, parity);
             parity ^= 1;
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // epilogue: warp w reads TMEM lanes 32 w .. + 31 (rows), all 128 columns
+            fence_after();
+            // read-back: warp (quarter, half) takes TMEM lanes 32 quarter .. + 31 (rows) and the column chunks
+            // half, half + 2, ...; the staging block overlays the A tiles, which the finished MMAs no longer read
             {
-                float *st = stage + warp * 32 * 33;
-                const int rbase = warp * 32, cbase = 0;
-#pragma unroll 1
-                for (int cc = 0; cc < 128; cc += 32) {
-                    uint32_t v[32];
-                    const uint32_t taddr = tmem + ((uint32_t)rbase << 16) + (uint32_t)(cbase + cc);
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-                          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-                          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                        : "r"(taddr));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int rbase = quarter * 32;
+                const bool full = u0 + rbase + 32 <= a.n_i;
+                for (int cc = half; cc < n_chunks; cc += 2) {
+                    float v[32];
+                    tmem_ld32(tmem + ((uint32_t)rbase << 16) + (uint32_t)(cc * 32), v);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) st[lane * 33 + j] = __uint_as_float(v[j]);
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4 *>(st + lane * kStageStride + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     __syncwarp();
-                    const int vcol = v0 + cbase + cc + lane;
-                    if (vcol < a.n_j) {
-#pragma unroll 8
-                        for (int rr = 0; rr < 32; ++rr) {
-                            const int u = u0 + rbase + rr;
-                            if (u < a.n_i) out[(size_t)u * a.n_j + vcol] = st[rr * 33 + lane];
+                    const int col = cc * 32 + lane, vcol = v0 + col;
+                    if (col < NT && vcol < a.n_j) {
+                        float *p = out + (size_t)(u0 + rbase) * a.n_j + vcol;
+                        if (full) {
+#pragma unroll
+                            for (int rr = 0; rr < 32; ++rr) {
+                                *p = st[rr * kStageStride + lane];
+                                p += a.n_j;
+                            }
+                        } else {
+                            for (int rr = 0; rr < 32 && u0 + rbase + rr < a.n_i; ++rr) p[(size_t)rr * a.n_j] = st[rr * kStageStride + lane];
                         }
                     }
                     __syncwarp();
                 }
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncthreads();  // TMEM and the A tile are free again
+            fence_before();
+            __syncthreads();  // TMEM and the A tiles / staging blocks are free again
         }
     }
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols));
+    if (warp == 0) tmem_dealloc<kTmemCols>(tmem);
 }
 
 }  // namespace
 
 void launch_predict_tc(const PredictArgs &a, int n_sm, cudaStream_t s) {
     if (a.count == 0 || a.n_i == 0 || a.n_j == 0) return;
-    const int n_nt = (a.n_j + kTileN - 1) / kTileN;
+    const int n_nt = (a.n_j + kMaxN - 1) / kMaxN;
+    const int NT = std::max(16, (((a.n_j + n_nt - 1) / n_nt) + 15) / 16 * 16);  // even split, MMA N granularity 16
     const int n_workers = std::max(1, std::min(a.count, 2 * n_sm / n_nt));
-    const size_t smem_bytes = 65536 + 4 * 32 * 33 * sizeof(float);
     static bool configured = false;
     if (!configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(predict_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        CUDA_CHECK(cudaFuncSetAttribute(predict_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         configured = true;
     }
-    predict_tc_kernel<<<n_nt * n_workers, kThreads, smem_bytes, s>>>(a, n_workers);
+    predict_tc_kernel<<<n_nt * n_workers, kThreads, kSmemBytes, s>>>(a, n_workers, NT);
     CUDA_CHECK(cudaGetLastError());
 }
 
