@@ -331,6 +331,25 @@ def run_ours(args):
         'kernels': phases,
         'loss_first_last': [float(losses[0]), float(losses[-1])],
     }
+    # The longest kernel of the step is the layer-1 backward SpMM of the many-relation group with the TF1 Adam of its
+    # weights fused in (the gradient never reaches HBM).  SURVEY.md 8(d): transposed CSR + dS + Adam state, "2.1 GB if
+    # fused into the dW epilogue" = read p, m, v and write p, m, v: 6 x 4 B per parameter instead of the dW1 write.
+    try:
+        bw = max((k for k in phases if k.startswith('spmm_bwd1')), key=lambda k: phases[k]['ms_per_step'])
+        gi = int(bw.rsplit('g', 1)[1])
+        g = list(inputs.edge_types)[gi]
+        K, n_j = inputs.edge_types[g], inputs.n_nodes[g[1]]
+        if world == 1 and K >= 8 and HYPER['dropout'] >= 0:
+            w1 = K * n_j * HYPER['hidden1'] * 4
+            fused = phases[bw]['bytes'] - w1 + 6 * w1
+            line['roofline_bwd1_fused_adam'] = {
+                'bound': 'hbm', 'kernel': bw + ' (spmm_tstaged_kernel<2>, Adam fused)', 'algorithmic_bytes': fused,
+                'ms': phases[bw]['ms_per_step'], 'achieved': fused / phases[bw]['ms_per_step'] / 1e6, 'peak': peak,
+                'unit': 'GB/s', 'frac': fused / phases[bw]['ms_per_step'] / 1e6 / peak,
+                'traffic': (json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json'))).get(bw)
+                            if args.config == 'poly' and args.scale == 1 else None)}
+    except Exception:
+        pass
     if world == 1 and args.config == 'poly' and args.scale == 1:
         # BASELINE config #4: all drug pairs x all drug-drug relation matrices from the current embeddings
         # (tcgen05 3 x TF32 kernel, output written to HBM; bound by the 3.2 GB it writes)

@@ -37,7 +37,7 @@ def build(force=False, verbose=False):
     os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
     for src in sources():
         obj = os.path.join(HERE, 'build', os.path.basename(src)[:-3] + '.o')
-        cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+        cmd = [NVCC] + FLAGS + os.environ.get('NVCC_EXTRA', '').split() + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     failed = False

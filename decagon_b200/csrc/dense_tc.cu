@@ -15,6 +15,8 @@
 // registers for the CTA's life (project), its dH sums live in registers (dh), the dW2 accumulator lives in TMEM
 // across the row tiles of a relation (dw2).  CTAs are sequential inside (build -> MMA -> read back); two CTAs per SM
 // overlap their phases.  hidden1 is 32 or 64 here (128 stays on the CUDA-core kernels of dense.cu), hidden2 = 32.
+#include <stdio.h>
+
 #include <algorithm>
 
 #include "dgn_internal.cuh"
@@ -27,6 +29,20 @@ using namespace tc;
 
 constexpr int kD2 = 32;
 constexpr int kThreads = 128;
+
+// Optional phase clock of project_tc_kernel (build with NVCC_EXTRA=-DDGN_TC_PROFILE): cycles summed over CTAs and
+// iterations for [operand writes, fence + barrier, MMA issue, wait for the MMAs, read-back + stores, closing barrier]
+#ifdef DGN_TC_PROFILE
+__device__ unsigned long long g_tc_prof[8];
+#define TC_CLK(i)                                   \
+    do {                                            \
+        const long long now__ = clock64();          \
+        prof_acc[i] += now__ - prof_t;              \
+        prof_t = now__;                             \
+    } while (0)
+#else
+#define TC_CLK(i) do { } while (0)
+#endif
 constexpr int kTile = 128;  // rows per tile = threads
 
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
@@ -54,13 +70,15 @@ __device__ __forceinline__ uint32_t tc_prologue(uint32_t *tmem_slot, uint64_t *b
 }
 
 // ------------------------------------------------------------------------------ P2 = Hm W2
-// CTA = (row tile, slot of relations).  smem: A [KB][hi, lo][128 x 128 B] K-major (thread = its own row, masked),
-// B [D1 / 8 k-blocks][hi, lo atoms of 8 x 128 B] MN-major: W2_k is [D1][32] row-major, i.e. N-contiguous, and is
-// copied as it lies.  The next relation's keep words and W2 are loaded right after the tiles are written, so
-// they fly during the MMAs and the read-back.
+// CTA = (row tile, slot of relations), 256 threads: thread = (row of the tile, half h).  smem: A [KB][hi, lo]
+// [128 x 128 B] K-major (masked rows), B [D1 / 8 k-blocks][hi, lo atoms] MN-major: W2_k is [D1][32] row-major, i.e.
+// N-contiguous, and is copied as it lies.  Half h of a row's threads writes half of the row's chunks and reads back
+// half of its output columns (the two warps of a TMEM lane quarter).  The next relation's keep words and W2 are
+// loaded right after the tiles are written, so they fly during the MMAs and the read-back.
+constexpr int kProjThreads = 256;
 template <int D1>
-__global__ void __launch_bounds__(kThreads, 2) project_tc_kernel(const DenseArgs a) {
-    constexpr int KB = D1 / 32, NW = D1 / 16;
+__global__ void __launch_bounds__(kProjThreads, 2) project_tc_kernel(const DenseArgs a) {
+    constexpr int KB = D1 / 32, NW = D1 / 32, NC = KB * 4;  // float4 of W2 per thread, chunks of the row per thread
     constexpr uint32_t kIdesc = idesc_tf32(128, 64, 0, 1);
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *As = smem;
@@ -68,37 +86,43 @@ __global__ void __launch_bounds__(kThreads, 2) project_tc_kernel(const DenseArgs
     __shared__ __align__(8) uint64_t mma_done;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int rl = tid & 127, h = tid >> 7;
     const int rt = blockIdx.x % a.n_rb, slot = blockIdx.x / a.n_rb;
-    const int row = rt * kTile + tid;
+    const int row = rt * kTile + rl;
     const bool valid = row < a.n_j;
     int k_begin, k_end;
     slot_range(slot, a.n_slots, a.K, k_begin, k_end);
     const uint32_t tmem = tc_prologue<64>(&tmem_slot, &mma_done, smem);
 
-    float4 x[KB][8];
+    // this thread's chunks of the row: global chunk index gc = h NC + c (panel gc >> 3, chunk gc & 7)
+    float4 x[NC];
 #pragma unroll
-    for (int p = 0; p < KB; ++p)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) x[p][c] = valid ? ld4(a.H + ((size_t)p * a.n_j + row) * 32 + 4 * c) : zero4();
+    for (int c = 0; c < NC; ++c) {
+        const int gc = h * NC + c;
+        x[c] = valid ? ld4(a.H + ((size_t)(gc >> 3) * a.n_j + row) * 32 + 4 * (gc & 7)) : zero4();
+    }
     const float sc = a.mask != nullptr ? a.scale : 1.f;
     uint32_t parity = 0;
-    uint32_t mk[KB];
+    uint32_t mk = 0xffffffffu;  // keep word of the panel this thread's chunks lie in (KB == 1: both halves share it)
     float4 w[NW];
+    const int mp = (h * NC) >> 3;  // panel of this thread's chunks
     auto fetch = [&](int k) {
-#pragma unroll
-        for (int p = 0; p < KB; ++p)
-            mk[p] = (a.mask != nullptr && valid) ? __ldg(a.mask + ((size_t)k * a.n_j + row) * KB + p) : 0xffffffffu;
+        mk = (a.mask != nullptr && valid) ? __ldg(a.mask + ((size_t)k * a.n_j + row) * KB + mp) : 0xffffffffu;
         const float *W = a.W2 + (size_t)k * D1 * kD2;
 #pragma unroll
-        for (int j = 0; j < NW; ++j) w[j] = ld4(W + 4 * (tid + kThreads * j));
+        for (int j = 0; j < NW; ++j) w[j] = ld4(W + 4 * (tid + kProjThreads * j));
     };
     if (k_begin < k_end) fetch(k_begin);
+#ifdef DGN_TC_PROFILE
+    long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_t = clock64();
+#endif
 
     for (int k = k_begin; k < k_end; ++k) {
         // B: float4 i of W2_k = (K index m = i >> 3, N chunk c = i & 7)
 #pragma unroll
         for (int j = 0; j < NW; ++j) {
-            const int i = tid + kThreads * j, m = i >> 3, c = i & 7;
+            const int i = tid + kProjThreads * j, m = i >> 3, c = i & 7;
             float4 hi, lo;
             split4(w[j], hi, lo);
             unsigned char *atom = Bs + (m >> 3) * 2048 + mn_off(m, c);
@@ -106,22 +130,23 @@ __global__ void __launch_bounds__(kThreads, 2) project_tc_kernel(const DenseArgs
             st128(atom + 1024, lo);
         }
 #pragma unroll
-        for (int p = 0; p < KB; ++p)
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                float4 v, hi, lo;
-                v.x = sel(mk[p], 4 * c + 0, x[p][c].x), v.y = sel(mk[p], 4 * c + 1, x[p][c].y);
-                v.z = sel(mk[p], 4 * c + 2, x[p][c].z), v.w = sel(mk[p], 4 * c + 3, x[p][c].w);
-                split4(v, hi, lo);
-                const uint32_t off = sw128(tid, c);
-                st128(As + (p * 2 + 0) * 16384 + off, hi);
-                st128(As + (p * 2 + 1) * 16384 + off, lo);
-            }
+        for (int c = 0; c < NC; ++c) {
+            const int gc = h * NC + c, cp = gc & 7;
+            float4 v, hi, lo;
+            v.x = sel(mk, 4 * cp + 0, x[c].x), v.y = sel(mk, 4 * cp + 1, x[c].y);
+            v.z = sel(mk, 4 * cp + 2, x[c].z), v.w = sel(mk, 4 * cp + 3, x[c].w);
+            split4(v, hi, lo);
+            const uint32_t off = sw128(rl, cp);
+            st128(As + ((gc >> 3) * 2 + 0) * 16384 + off, hi);
+            st128(As + ((gc >> 3) * 2 + 1) * 16384 + off, lo);
+        }
         if (k + 1 < k_end) fetch(k + 1);
+        TC_CLK(0);
         fence_async_smem();
         fence_before();
         __syncthreads();
-        if (tid == 0) {
+        TC_CLK(1);
+        if (warp == 0) {  // the whole warp, convergent: one elected lane issues (tc_common.cuh)
             fence_after();
 #pragma unroll
             for (int p = 0; p < KB; ++p) {
@@ -129,32 +154,43 @@ __global__ void __launch_bounds__(kThreads, 2) project_tc_kernel(const DenseArgs
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                     const uint64_t b = umma_desc_mn(smem_u32(Bs + (p * 4 + ks) * 2048), 1024);
-                    mma_tf32(tmem, ahi + 2 * ks, b, kIdesc, (p | ks) != 0);
-                    mma_tf32(tmem, alo + 2 * ks, b, kIdesc, 1);
+                    mma_tf32_elect(tmem, ahi + 2 * ks, b, kIdesc, (p | ks) != 0);
+                    mma_tf32_elect(tmem, alo + 2 * ks, b, kIdesc, 1);
                 }
             }
-            mma_commit(&mma_done);
+            mma_commit_elect(&mma_done);
         }
+        TC_CLK(2);
         mbar_wait(&mma_done, parity);
         parity ^= 1;
         fence_after();
+        TC_CLK(3);
         {
-            float v0[32], v1[32];
-            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-            tmem_ld32(taddr, v0);
-            tmem_ld32(taddr + 32, v1);
+            // warp = (lane quarter warp & 3 = rl >> 5, half h): output columns [16 h, 16 h + 16)
+            float v0[16], v1[16];
+            const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 16 * h;
+            tmem_ld16(taddr, v0);
+            tmem_ld16(taddr + 32, v1);
             if (valid) {
-                float *dst = a.P2 + ((size_t)k * a.n_j + row) * kD2;
+                float *dst = a.P2 + ((size_t)k * a.n_j + row) * kD2 + 16 * h;
 #pragma unroll
-                for (int c = 0; c < 8; ++c)
+                for (int c = 0; c < 4; ++c)
                     *reinterpret_cast<float4 *>(dst + 4 * c) =
                         make_float4((v0[4 * c] + v1[4 * c]) * sc, (v0[4 * c + 1] + v1[4 * c + 1]) * sc,
                                     (v0[4 * c + 2] + v1[4 * c + 2]) * sc, (v0[4 * c + 3] + v1[4 * c + 3]) * sc);
             }
         }
+        TC_CLK(4);
         fence_before();
         __syncthreads();  // TMEM and the operand tiles are free again
+        TC_CLK(5);
     }
+#ifdef DGN_TC_PROFILE
+    if (tid == 0) {
+        for (int i = 0; i < 6; ++i) atomicAdd(&g_tc_prof[i], (unsigned long long)prof_acc[i]);
+        atomicAdd(&g_tc_prof[6], (unsigned long long)(k_end - k_begin));
+    }
+#endif
     if (warp == 0) tmem_dealloc<64>(tmem);
 }
 
@@ -423,11 +459,23 @@ void launch_project_tc(const DenseArgs &a, int D1, cudaStream_t s) {
     if (D1 == 64) {
         const size_t bytes = 2 * 2 * 16384 + 2 * 8192;
         set_smem(project_tc_kernel<64>, bytes);
-        project_tc_kernel<64><<<a.n_rb * a.n_slots, kThreads, bytes, s>>>(a);
+        project_tc_kernel<64><<<a.n_rb * a.n_slots, kProjThreads, bytes, s>>>(a);
+#ifdef DGN_TC_PROFILE
+        if (a.K > 100) {
+            unsigned long long h[8];
+            cudaStreamSynchronize(s);
+            cudaMemcpyFromSymbol(h, g_tc_prof, sizeof(h));
+            const double it = (double)h[6];
+            fprintf(stderr, "project_tc phases (thread 0, cycles per CTA-iteration over %.0f): writes %.0f  fence+bar %.0f  issue %.0f  "
+                            "wait %.0f  readback %.0f  bar %.0f\n", it, h[0] / it, h[1] / it, h[2] / it, h[3] / it, h[4] / it, h[5] / it);
+            unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            cudaMemcpyToSymbol(g_tc_prof, z, sizeof(z));
+        }
+#endif
     } else {
         const size_t bytes = 2 * 16384 + 8192;
         set_smem(project_tc_kernel<32>, bytes);
-        project_tc_kernel<32><<<a.n_rb * a.n_slots, kThreads, bytes, s>>>(a);
+        project_tc_kernel<32><<<a.n_rb * a.n_slots, kProjThreads, bytes, s>>>(a);
     }
     CUDA_CHECK(cudaGetLastError());
 }
