@@ -392,14 +392,31 @@ __global__ void __launch_bounds__(DenseCfg<D1>::NT2, 1) dw2_kernel(const DenseAr
     }
 }
 
-__global__ void dw2_reduce_kernel(const float *__restrict__ part, float *__restrict__ out, int n_chunks, int elems,
-                                  long long total) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const long long k = i / elems, e = i % elems;
-    float s = 0.f;
-    for (int c = 0; c < n_chunks; ++c) s += part[(k * n_chunks + c) * elems + e];
-    out[i] = s;
+// out[k][e] = sum over the n_chunks partials, in a fixed order: CTA = (k, block of 32 elements), warp w sums a
+// contiguous range of chunks (four loads in flight), the 8 range sums are added in warp order.
+__global__ void __launch_bounds__(256) dw2_reduce_kernel(const float *__restrict__ part, float *__restrict__ out, int n_chunks, int elems) {
+    __shared__ float red[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int blocks_per_k = elems / 32;
+    const long long k = blockIdx.x / blocks_per_k;
+    const int e = (blockIdx.x % blocks_per_k) * 32 + lane;
+    const int per = (n_chunks + 7) / 8, c0 = warp * per, c1 = min(c0 + per, n_chunks);
+    const float *src = part + (k * n_chunks) * elems + e;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int c = c0;
+    for (; c + 4 <= c1; c += 4) {
+        s0 += src[(size_t)c * elems], s1 += src[(size_t)(c + 1) * elems];
+        s2 += src[(size_t)(c + 2) * elems], s3 += src[(size_t)(c + 3) * elems];
+    }
+    for (; c < c1; ++c) s0 += src[(size_t)c * elems];
+    red[warp][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (warp == 0) {
+        float s = red[0][lane];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) s += red[w][lane];
+        out[k * elems + e] = s;
+    }
 }
 
 template <int D1>
@@ -454,9 +471,9 @@ void launch_dw2(const DenseArgs &a, int D1, int D2, cudaStream_t s) {
 }
 
 void launch_dw2_reduce(const float *part, float *out, int K, int n_chunks, int elems, cudaStream_t s) {
-    const long long total = (long long)K * elems;
-    if (total == 0) return;
-    dw2_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(part, out, n_chunks, elems, total);
+    if ((long long)K * elems == 0) return;
+    DGN_REQUIRE(elems % 32 == 0, "dw2 reduce: %d elements per relation", elems);
+    dw2_reduce_kernel<<<(unsigned)(K * (elems / 32)), 256, 0, s>>>(part, out, n_chunks, elems);
     CUDA_CHECK(cudaGetLastError());
 }
 

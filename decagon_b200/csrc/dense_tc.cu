@@ -16,6 +16,7 @@
 // across the row tiles of a relation (dw2).  CTAs are sequential inside (build -> MMA -> read back); two CTAs per SM
 // overlap their phases.  hidden1 is 32 or 64 here (128 stays on the CUDA-core kernels of dense.cu), hidden2 = 32.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -192,6 +193,122 @@ __global__ void __launch_bounds__(kProjThreads, 2) project_tc_kernel(const Dense
     }
 #endif
     if (warp == 0) tmem_dealloc<64>(tmem);
+}
+
+// ------------------------------------------------------------------------------ P2 = Hm W2, A in tensor memory
+// Same geometry as project_tc_kernel; the masked, split rows go to TENSOR memory (tcgen05.st: lane = the thread's
+// row, one column per K element, no swizzle arithmetic, 256 B / clk) and the MMAs take A from there (TS form).
+// Shared memory only carries B (16 KB written, 32 KB read per relation instead of 80 + 96 KB), so the MMA is no
+// longer paced by operand reads.  TMEM columns: D [0, 64), A hi [64, 64 + D1), A lo [64 + D1, 64 + 2 D1).
+// D1 = 64 only (each of the two threads of a row holds one 32-wide panel = one tcgen05.st.x32 per part).
+__global__ void __launch_bounds__(kProjThreads, 2) project_ts_kernel(const DenseArgs a) {
+    constexpr int D1 = 64, KB = 2, NW = 2;
+    constexpr uint32_t kIdesc = idesc_tf32(128, 64, 0, 1);
+    constexpr uint32_t kAhi = 64, kAlo = 64 + D1;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *Bs = smem;
+    __shared__ __align__(8) uint64_t mma_done;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int rl = tid & 127, h = tid >> 7;
+    const int rt = blockIdx.x % a.n_rb, slot = blockIdx.x / a.n_rb;
+    const int row = rt * kTile + rl;
+    const bool valid = row < a.n_j;
+    int k_begin, k_end;
+    slot_range(slot, a.n_slots, a.K, k_begin, k_end);
+    const uint32_t tmem = tc_prologue<256>(&tmem_slot, &mma_done, smem);
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+
+    float x[32];  // panel h of this thread's row
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float4 v = valid ? ld4(a.H + ((size_t)h * a.n_j + row) * 32 + 4 * c) : zero4();
+        x[4 * c] = v.x, x[4 * c + 1] = v.y, x[4 * c + 2] = v.z, x[4 * c + 3] = v.w;
+    }
+    const float sc = a.mask != nullptr ? a.scale : 1.f;
+    uint32_t parity = 0;
+    uint32_t mk = 0xffffffffu;
+    float4 w[NW];
+    auto fetch = [&](int k) {
+        mk = (a.mask != nullptr && valid) ? __ldg(a.mask + ((size_t)k * a.n_j + row) * KB + h) : 0xffffffffu;
+        const float *W = a.W2 + (size_t)k * D1 * kD2;
+#pragma unroll
+        for (int j = 0; j < NW; ++j) w[j] = ld4(W + 4 * (tid + kProjThreads * j));
+    };
+    if (k_begin < k_end) fetch(k_begin);
+#ifdef DGN_TC_PROFILE
+    long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_t = clock64();
+#endif
+
+    for (int k = k_begin; k < k_end; ++k) {
+#pragma unroll
+        for (int j = 0; j < NW; ++j) {
+            const int i = tid + kProjThreads * j, m = i >> 3, c = i & 7;
+            float4 hi, lo;
+            split4(w[j], hi, lo);
+            unsigned char *atom = Bs + (m >> 3) * 2048 + mn_off(m, c);
+            st128(atom, hi);
+            st128(atom + 1024, lo);
+        }
+        {
+            float hi[32], lo[32];
+#pragma unroll
+            for (int f = 0; f < 32; ++f) {
+                const float v = sel(mk, f, x[f]);
+                hi[f] = tf32_hi(v);
+                lo[f] = v - hi[f];
+            }
+            tmem_st32(lane_base + kAhi + 32 * h, hi);
+            tmem_st32(lane_base + kAlo + 32 * h, lo);
+            tmem_st_wait();
+        }
+        if (k + 1 < k_end) fetch(k + 1);
+        TC_CLK(0);
+        fence_async_smem();
+        fence_before();
+        __syncthreads();
+        TC_CLK(1);
+        if (warp == 0) {
+            fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const uint64_t b = umma_desc_mn(smem_u32(Bs + ks * 2048), 1024);
+                mma_tf32_ts_elect(tmem, tmem + kAhi + 8 * ks, b, kIdesc, ks != 0);
+                mma_tf32_ts_elect(tmem, tmem + kAlo + 8 * ks, b, kIdesc, 1);
+            }
+            mma_commit_elect(&mma_done);
+        }
+        TC_CLK(2);
+        mbar_wait(&mma_done, parity);
+        parity ^= 1;
+        fence_after();
+        TC_CLK(3);
+        {
+            float v0[16], v1[16];
+            tmem_ld16(lane_base + 16 * h, v0);
+            tmem_ld16(lane_base + 32 + 16 * h, v1);
+            if (valid) {
+                float *dst = a.P2 + ((size_t)k * a.n_j + row) * kD2 + 16 * h;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    *reinterpret_cast<float4 *>(dst + 4 * c) =
+                        make_float4((v0[4 * c] + v1[4 * c]) * sc, (v0[4 * c + 1] + v1[4 * c + 1]) * sc,
+                                    (v0[4 * c + 2] + v1[4 * c + 2]) * sc, (v0[4 * c + 3] + v1[4 * c + 3]) * sc);
+            }
+        }
+        TC_CLK(4);
+        fence_before();
+        __syncthreads();  // the accumulator, the A columns and the B tile are free again
+        TC_CLK(5);
+    }
+#ifdef DGN_TC_PROFILE
+    if (tid == 0) {
+        for (int i = 0; i < 6; ++i) atomicAdd(&g_tc_prof[i], (unsigned long long)prof_acc[i]);
+        atomicAdd(&g_tc_prof[6], (unsigned long long)(k_end - k_begin));
+    }
+#endif
+    if (warp == 0) tmem_dealloc<256>(tmem);
 }
 
 // ------------------------------------------------------------------------------ dH += (G2 W2^T) (.) m
@@ -456,7 +573,22 @@ int dense_tc_tiles(int n_j) { return (n_j + kTile - 1) / kTile; }
 // a.n_rb = row tiles of 128, a.n_slots = CTAs per row tile
 void launch_project_tc(const DenseArgs &a, int D1, cudaStream_t s) {
     if (a.K == 0 || a.n_j == 0) return;
-    if (D1 == 64) {
+    const char *ss = getenv("DGN_PROJECT_SS");  // 1: both operands from shared memory (project_tc_kernel)
+    if (D1 == 64 && !(ss && ss[0] == '1')) {
+        project_ts_kernel<<<a.n_rb * a.n_slots, kProjThreads, 16384, s>>>(a);
+#ifdef DGN_TC_PROFILE
+        if (a.K > 100) {
+            unsigned long long h[8];
+            cudaStreamSynchronize(s);
+            cudaMemcpyFromSymbol(h, g_tc_prof, sizeof(h));
+            const double it = (double)h[6];
+            fprintf(stderr, "project_ts phases (thread 0, cycles per CTA-iteration over %.0f): writes %.0f  fence+bar %.0f  issue %.0f  "
+                            "wait %.0f  readback %.0f  bar %.0f\n", it, h[0] / it, h[1] / it, h[2] / it, h[3] / it, h[4] / it, h[5] / it);
+            unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            cudaMemcpyToSymbol(g_tc_prof, z, sizeof(z));
+        }
+#endif
+    } else if (D1 == 64) {
         const size_t bytes = 2 * 2 * 16384 + 2 * 8192;
         set_smem(project_tc_kernel<64>, bytes);
         project_tc_kernel<64><<<a.n_rb * a.n_slots, kProjThreads, bytes, s>>>(a);

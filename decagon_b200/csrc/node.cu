@@ -42,9 +42,23 @@ __global__ void __launch_bounds__(256) node_epilogue_kernel(const EpiArgs a) {
                 for (int p = 0; p < P; ++p) s[p] += g.peer[r][((size_t)p * a.n_rows + row) * 32 + lane];
         } else if (g.row_seg_ptr != nullptr) {
             const int s0 = g.row_seg_ptr[row], s1 = g.row_seg_ptr[row + 1];
-            for (int sg = s0; sg < s1; ++sg)
+            float b1[P], b2[P], b3[P];  // four interleaved partial sums: hub rows span many segments
+#pragma unroll
+            for (int p = 0; p < P; ++p) b1[p] = b2[p] = b3[p] = 0.f;
+            int sg = s0;
+            for (; sg + 4 <= s1; sg += 4)
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    s[p] += g.partial[((size_t)sg * P + p) * 32 + lane];
+                    b1[p] += g.partial[((size_t)(sg + 1) * P + p) * 32 + lane];
+                    b2[p] += g.partial[((size_t)(sg + 2) * P + p) * 32 + lane];
+                    b3[p] += g.partial[((size_t)(sg + 3) * P + p) * 32 + lane];
+                }
+            for (; sg < s1; ++sg)
 #pragma unroll
                 for (int p = 0; p < P; ++p) s[p] += g.partial[((size_t)sg * P + p) * 32 + lane];
+#pragma unroll
+            for (int p = 0; p < P; ++p) s[p] = (s[p] + b1[p]) + (b2[p] + b3[p]);
         } else {
             for (int sl = 0; sl < g.n_slots; ++sl)
 #pragma unroll

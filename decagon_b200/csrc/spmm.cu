@@ -112,12 +112,25 @@ __global__ void __launch_bounds__(256) seg_reduce_kernel(const SpmmArgs a, const
     if (w >= n_multi) return;
     const int row = multi_rows[w];
     const int s0 = a.row_seg_ptr[row], s1 = a.row_seg_ptr[row + 1];
-    float acc[P];
+    // four interleaved partial sums (a fixed order all the same): hub rows span hundreds of segments and a
+    // single dependent chain pays one L2 round trip per segment
+    float acc[P], b1[P], b2[P], b3[P];
 #pragma unroll
-    for (int p = 0; p < P; ++p) acc[p] = 0.f;
-    for (int s = s0; s < s1; ++s)
+    for (int p = 0; p < P; ++p) acc[p] = b1[p] = b2[p] = b3[p] = 0.f;
+    int s = s0;
+    for (; s + 4 <= s1; s += 4)
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            acc[p] += a.partial[((size_t)s * P + p) * 32 + lane];
+            b1[p] += a.partial[((size_t)(s + 1) * P + p) * 32 + lane];
+            b2[p] += a.partial[((size_t)(s + 2) * P + p) * 32 + lane];
+            b3[p] += a.partial[((size_t)(s + 3) * P + p) * 32 + lane];
+        }
+    for (; s < s1; ++s)
 #pragma unroll
         for (int p = 0; p < P; ++p) acc[p] += a.partial[((size_t)s * P + p) * 32 + lane];
+#pragma unroll
+    for (int p = 0; p < P; ++p) acc[p] = (acc[p] + b1[p]) + (b2[p] + b3[p]);
     float sc = 1.f;
     if (a.row_mask) sc = mask_bit(a.mask, row) ? a.scale : 0.f;
 #pragma unroll
