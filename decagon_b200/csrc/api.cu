@@ -378,6 +378,8 @@ struct dgn_graph {
     int staged_version = 3;
     cudaStream_t stream = nullptr;   // lane 0: groups of many small relations (staged kernels), decode, Adam
     cudaStream_t stream2 = nullptr;  // lane 1: the other groups; ordered against lane 0 by events per tensor
+    cudaStream_t stream3 = nullptr;  // layer-2 keep words of every group (integer ALU work beside lane 1's gathers)
+    cudaEvent_t mask_go = nullptr, mask_done = nullptr;
     bool own_stream = false;
     int rank = 0, world = 1;
     bool arena_ready = false;
@@ -740,10 +742,31 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step, StepDep
             cudaStream_t s = lane_stream(g, G.lane);
             launch_gen_mask(G.mask1, G.mask1_words, G.feat_nnz, 0, G.rel_ids, kStreamDropout1, step, seed, thr, s);
             g->launches++;
+            // the layer-2 keep words of every group are drawn on a third, low-priority stream: integer ALU work that
+            // runs beside lane 1's L2-bound layer-1 SpMMs; the first staged kernel and every projection wait for it
+            if (g->two_lanes) continue;
             launch_gen_mask(G.mask2, G.mask2_words, (long long)G.n_j * g->d1, G.n_j * P1, G.rel_ids, kStreamDropout2, step, seed, thr, s);
             g->launches++;
         }
+        if (g->two_lanes) {
+            CUDA_CHECK(cudaEventRecord(g->mask_go, g->stream));  // after the join: last step's readers of mask2 are done
+            CUDA_CHECK(cudaStreamWaitEvent(g->stream3, g->mask_go, 0));
+            for (int lane = 1; lane >= 0; --lane)  // small ones first
+                for (auto &G : g->groups) {
+                    if (G.lane != lane) continue;
+                    launch_gen_mask(G.mask2, G.mask2_words, (long long)G.n_j * g->d1, G.n_j * P1, G.rel_ids, kStreamDropout2, step, seed,
+                                    thr, g->stream3);
+                    g->launches++;
+                }
+            CUDA_CHECK(cudaEventRecord(g->mask_done, g->stream3));
+        }
     }
+    bool mask_waited[2] = {!(drop && g->two_lanes), !(drop && g->two_lanes)};
+    auto wait_mask2 = [&](int lane) {
+        if (mask_waited[lane]) return;
+        CUDA_CHECK(cudaStreamWaitEvent(lane_stream(g, lane), g->mask_done, 0));
+        mask_waited[lane] = true;
+    };
     auto spmm_fwd = [&](Group &G, const float *op, int P, long long op_rows, float *part, const SlotTable &slots,
                         const int *wstart, const uint32_t *mask) {
         cudaStream_t s = lane_stream(g, G.lane);
@@ -805,9 +828,27 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step, StepDep
     };
     // lane 0 groups first: their kernels are the long ones.  On lane 1 the groups whose ROW type is summed on lane 0
     // come first: lane 0 waits for exactly those partial sums before it can go on
-    const std::vector<int> order = lane_order(g, false);
+    // The persistent staged kernels of lane 0 fill every SM (1024 threads x 64 registers): whatever lane 1 has queued
+    // starves until they finish.  So lane 1's kernels of a layer are issued FIRST, where they overlap lane 0's mask
+    // generation (integer ALU against L2-bound gathers) and its tensor-core projection (which leaves room), and the
+    // staged kernel of the layer waits for them ("gate"): lane 1 then holds its results by the time lane 0 needs them.
+    std::vector<int> order;
+    {
+        const std::vector<int> lo = lane_order(g, false);
+        for (int gi : lo)
+            if (g->groups[gi].lane == 1) order.push_back(gi);
+        for (int gi : lo)
+            if (g->groups[gi].lane == 0) order.push_back(gi);
+    }
+    auto gate = [&](Group &G, std::vector<Dep> &deps) {  // lane 0 waits for every lane-1 group's partial sums
+        if (G.lane != 0 || !G.staged) return;
+        for (int q = 0; q < g->n_groups; ++q)
+            if (g->groups[q].lane == 1) consume(g, deps[q], 0);
+        wait_mask2(0);  // or the staged kernel would starve the mask generation as well
+    };
     for (int gi : order) {
         Group &G = g->groups[gi];
+        gate(G, D.S1);
         {
             PhaseScope ph(g, "spmm_fwd1", gi, G.lane);
             if (G.gen_feat) {  // P1_k = (X_j (.) m_k / q) W1_k, then the SpMM on P1 like layer 2 on P2
@@ -832,6 +873,7 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step, StepDep
     for (int gi : order) {
         Group &G = g->groups[gi];
         consume(g, D.H[G.j], G.lane);
+        wait_mask2(G.lane);
         {
             PhaseScope ph(g, "project", gi, G.lane);
             DenseArgs a = {};
@@ -842,6 +884,7 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step, StepDep
             else launch_project(a, g->d1, g->d2, lane_stream(g, G.lane));
             g->launches++;
         }
+        gate(G, D.S2);
         {
             PhaseScope ph(g, "spmm_fwd2", gi, G.lane);
             spmm_fwd(G, G.P2, 1, (long long)G.Kl * G.n_j, G.part2, G.slots2, G.wstart2, nullptr);
@@ -1295,6 +1338,9 @@ extern "C" int dgn_graph_create(dgn_graph **out, int device, int n_types, const 
         CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CUDA_CHECK(cudaStreamCreateWithPriority(&g->stream, cudaStreamNonBlocking, hi));
         CUDA_CHECK(cudaStreamCreateWithPriority(&g->stream2, cudaStreamNonBlocking, lo));
+        CUDA_CHECK(cudaStreamCreateWithPriority(&g->stream3, cudaStreamNonBlocking, lo));
+        CUDA_CHECK(cudaEventCreateWithFlags(&g->mask_go, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&g->mask_done, cudaEventDisableTiming));
     }
     g->own_stream = true;
     for (int i = 0; i < dgn_graph::kRing; ++i) CUDA_CHECK(cudaEventCreateWithFlags(&g->ring_ev[i], cudaEventDisableTiming));
@@ -1368,6 +1414,9 @@ extern "C" int dgn_graph_destroy(dgn_graph *g) {
     for (auto &e : g->dep_events) cudaEventDestroy(e);
     if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
     if (g->stream2) cudaStreamDestroy(g->stream2);
+    if (g->stream3) cudaStreamDestroy(g->stream3);
+    if (g->mask_go) cudaEventDestroy(g->mask_go);
+    if (g->mask_done) cudaEventDestroy(g->mask_done);
     delete g;
     DGN_API_END
 }
