@@ -57,6 +57,7 @@ SIGNATURES = {
     'dgn_predict_edges': (ctypes.c_int, [c_graph, ctypes.c_int, c_i32p, ctypes.c_int32, ctypes.c_int, c_f32p]),
     'dgn_evaluate_edges': (ctypes.c_int, [c_graph, ctypes.c_int, ctypes.c_int64, c_i32p, c_i32p,
                                           ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, c_f32p, c_f64p, c_f64p]),
+    'dgn_rank_edges': (ctypes.c_int, [c_graph, ctypes.c_int, c_i32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, c_i32p, c_f32p]),
     'dgn_tensor_get': (ctypes.c_int, [c_graph, ctypes.c_int, ctypes.c_int, c_f32p, ctypes.c_int64]),
     'dgn_tensor_set': (ctypes.c_int, [c_graph, ctypes.c_int, ctypes.c_int, c_f32p, ctypes.c_int64]),
     'dgn_relation_matrices': (ctypes.c_int, [c_graph, ctypes.c_int, c_f32p, c_f32p]),

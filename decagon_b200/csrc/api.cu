@@ -1947,6 +1947,46 @@ extern "C" int dgn_evaluate_edges(dgn_graph *g, int group, int64_t n_edges, cons
     DGN_API_END
 }
 
+// GreedyActiveLearner._getRankedPossibilities: candidates of ONE relation scored on the device and ranked there
+extern "C" int dgn_rank_edges(dgn_graph *g, int r, const int32_t *edges, int64_t n_edges, int apply_sigmoid, int64_t top,
+                              int32_t *order_out, float *scores_out) {
+    DGN_API_BEGIN
+    check_finalized(g);
+    DGN_REQUIRE(n_edges >= 0 && n_edges < (int64_t)INT32_MAX && top >= 0 && top <= n_edges, "bad sizes: %lld candidates, top %lld",
+                (long long)n_edges, (long long)top);
+    DGN_REQUIRE(n_edges == 0 || (edges && (top == 0 || order_out)), "null argument");
+    if (n_edges == 0 || top == 0) return DGN_OK;
+    CUDA_CHECK(cudaSetDevice(g->device));
+    PredictArgs a = predict_args(g, r, 1);
+    for (int64_t e = 0; e < n_edges; ++e)
+        DGN_REQUIRE(edges[2 * e] >= 0 && edges[2 * e] < a.n_i && edges[2 * e + 1] >= 0 && edges[2 * e + 1] < a.n_j,
+                    "candidate %lld = (%d, %d) outside %d x %d", (long long)e, edges[2 * e], edges[2 * e + 1], a.n_i, a.n_j);
+    int *e_dev = nullptr, *idx = nullptr, *order = nullptr;
+    float *s_dev = nullptr, *ss_dev = nullptr;
+    void *tmp = nullptr;
+    auto release = [&]() { cudaFree(e_dev), cudaFree(idx), cudaFree(order), cudaFree(s_dev), cudaFree(ss_dev), cudaFree(tmp); };
+    try {
+        PhaseScope ph(g, "rank");
+        e_dev = dev_alloc<int>((size_t)n_edges * 2);
+        idx = dev_alloc<int>((size_t)n_edges), order = dev_alloc<int>((size_t)n_edges);
+        s_dev = dev_alloc<float>((size_t)n_edges), ss_dev = dev_alloc<float>((size_t)n_edges);
+        const size_t tmp_bytes = rank_sort_bytes(n_edges);
+        tmp = dev_alloc<unsigned char>(tmp_bytes ? tmp_bytes : 1);
+        CUDA_CHECK(cudaMemcpyAsync(e_dev, edges, (size_t)n_edges * 2 * sizeof(int), cudaMemcpyHostToDevice, g->stream));
+        launch_predict_edges(a, e_dev, (int)n_edges, apply_sigmoid, s_dev, g->stream);
+        launch_rank(s_dev, n_edges, idx, ss_dev, order, tmp, tmp_bytes, g->stream);
+        g->launches += 3;
+        CUDA_CHECK(cudaMemcpyAsync(order_out, order, (size_t)top * sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+        if (scores_out) CUDA_CHECK(cudaMemcpyAsync(scores_out, ss_dev, (size_t)top * sizeof(float), cudaMemcpyDeviceToHost, g->stream));
+        CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    } catch (...) {
+        release();
+        throw;
+    }
+    release();
+    DGN_API_END
+}
+
 extern "C" int dgn_tensor_get(dgn_graph *g, int which, int index, float *out, int64_t n) {
     DGN_API_BEGIN
     check_finalized(g);

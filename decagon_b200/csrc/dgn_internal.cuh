@@ -269,6 +269,9 @@ void launch_predict_edges(const PredictArgs &a, const int *edges, int n_edges, i
 void launch_predict_edges_multi(const PredictArgs &a, const int *rel_k, const int *edges, long long n_edges,
                                 int apply_sigmoid, float *out, cudaStream_t s);  // evaluate.cu
 size_t auc_sort_bytes(long long n);
+size_t rank_sort_bytes(long long n);
+void launch_rank(const float *scores, long long n, int *idx_in, float *sorted_scores, int *order, void *tmp, size_t tmp_bytes,
+                 cudaStream_t s);
 void launch_auc(const float *scores, const unsigned char *labels, long long n, float *sorted_scores,
                 unsigned char *sorted_labels, void *tmp, size_t tmp_bytes, double *out, cudaStream_t s);
 void launch_adam(float *p, const float *g, float *m, float *v, long long n, float alpha, float one_minus_b1,

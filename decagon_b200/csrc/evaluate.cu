@@ -4,6 +4,8 @@
 // roc_auc_score / average_precision_score definitions: distinct-threshold ROC trapezoid, step-wise AP).
 #include <cub/device/device_radix_sort.cuh>
 
+#include <algorithm>
+
 #include "dgn_internal.cuh"
 
 namespace dgn {
@@ -112,7 +114,26 @@ __global__ void __launch_bounds__(kAucThreads) auc_kernel(const float *__restric
     }
 }
 
+__global__ void iota_kernel(int *__restrict__ idx, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) idx[i] = (int)i;
+}
+
 }  // namespace
+
+// candidate ranking (GreedyActiveLearner._getRankedPossibilities, main/ActiveLearner/GreedyActiveLearner.py:84-92):
+// argsort of the scores in descending order, stable (ties keep their input order)
+size_t rank_sort_bytes(long long n) {
+    size_t bytes = 0;
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, (const float *)nullptr, (float *)nullptr, (const int *)nullptr,
+                                                         (int *)nullptr, n));
+    return bytes;
+}
+void launch_rank(const float *scores, long long n, int *idx_in, float *sorted_scores, int *order, void *tmp, size_t tmp_bytes,
+                 cudaStream_t s) {
+    iota_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, s>>>(idx_in, n);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, scores, sorted_scores, idx_in, order, n, 0, 32, s));
+}
 
 void launch_predict_edges_multi(const PredictArgs &a, const int *rel_k, const int *edges, long long n_edges,
                                 int apply_sigmoid, float *out, cudaStream_t s) {

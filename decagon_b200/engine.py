@@ -273,6 +273,17 @@ class Engine(object):
             ctypes.byref(auroc) if lab is not None else None, ctypes.byref(auprc) if lab is not None else None))
         return scores, auroc.value, auprc.value
 
+    def rank_edges(self, r, edges, top=None, sigmoid=True):
+        """Indices of the ``top`` best-scoring candidates of relation r in descending score order, and their scores
+        (GreedyActiveLearner._getRankedPossibilities, GreedyActiveLearner.py:84-92), scored and sorted on the device."""
+        edges = as_i32(np.asarray(edges).reshape(-1, 2))
+        top = len(edges) if top is None else min(int(top), len(edges))
+        order = np.empty(top, dtype=np.int32)
+        scores = np.empty(top, dtype=np.float32)
+        check(self.lib.dgn_rank_edges(self._h, int(r), ptr(edges, ctypes.c_int32), len(edges), 1 if sigmoid else 0, top,
+                                      ptr(order, ctypes.c_int32), ptr(scores, ctypes.c_float)))
+        return order, scores
+
     def tensor(self, which, index):
         if which in (_lib.TENSOR_HIDDEN1, _lib.TENSOR_EMBEDDINGS, _lib.TENSOR_GRAD_EMBEDDINGS):
             rows = self.n_nodes[index]

@@ -185,6 +185,14 @@ int dgn_evaluate_edges(dgn_graph *g, int group, int64_t n_edges, const int32_t *
                        const uint8_t *labels, int apply_sigmoid, float *scores_out, double *auroc_out,
                        double *auprc_out);
 
+/* GreedyActiveLearner._getRankedPossibilities (main/ActiveLearner/GreedyActiveLearner.py:84-92: sigmoid of the
+ * predictions of one relation, np.take at the candidate coordinates, np.argsort(...)[::-1]) without the [n_i, n_j]
+ * matrix: the candidates edges[2e], edges[2e+1] of relation r are scored and sorted on the device;
+ * order_out[0 .. top) = indices of the best candidates in descending score order (ties in input order),
+ * scores_out (may be NULL) their scores. */
+int dgn_rank_edges(dgn_graph *g, int r, const int32_t *edges, int64_t n_edges, int apply_sigmoid, int64_t top,
+                   int32_t *order_out, float *scores_out);
+
 /* model.embeddings[t], model.hidden1[t], per-group layer outputs (DecagonLogger.py:239-242) */
 int dgn_tensor_get(dgn_graph *g, int which, int index, float *out, int64_t n);
 

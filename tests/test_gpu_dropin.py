@@ -318,3 +318,36 @@ def test_ndarray_dumps_and_variable_checkpoints(tmp_path):
     with pytest.raises(KeyError):
         ndarray_io.load_variables(sess2, model2, str(tmp_path / 'partial.npz'))
     assert len(ndarray_io.load_variables(sess2, model2, str(tmp_path / 'partial.npz'), strict=False)) == 3
+
+
+def test_greedy_candidate_ranking_on_device():
+    """GreedyActiveLearner._getRankedPossibilities (GreedyActiveLearner.py:84-92) on the device against the
+    reference's own sequence: sigmoid(predictions of (1, 1, 0)), np.take at row * n_cols + col, argsort descending."""
+    from decagon_b200.active_learning import GreedyCandidateRanker, num_to_unmask
+    from decagon_b200.evaluator import sigmoid
+    case = common.Case(datasets.toy_graph())
+    eng = case.engine()
+    eng.forward(0.0, 0, 0)
+    r = case.it.edge_type2idx[1, 1, 0]
+    rng = np.random.RandomState(5)
+    n1 = case.inputs.n_nodes[1]
+    poss = np.column_stack([rng.randint(0, 3, 30000), rng.randint(0, n1, 30000), rng.randint(0, n1, 30000)])
+    ranker = GreedyCandidateRanker(eng, poss, r)
+    pred = sigmoid(eng.predict(r))
+    ref_scores = np.take(pred, poss[:, 1] * n1 + poss[:, 2])
+    order = ranker.ranked_possibilities()
+    assert sorted(order.tolist()) == list(range(len(poss)))
+    got = ref_scores[order]
+    assert np.all(np.diff(got) <= 1e-6)  # descending, up to the rounding between the two score paths
+    top = ranker.get_new_sample_idxs(100)
+    assert np.array_equal(top, order[:100])
+    # the same set as the reference's argsort, away from near-ties at the cut
+    ref_order = np.argsort(ref_scores)[::-1]
+    cut = ref_scores[ref_order[99]]
+    clear = ref_scores[ref_order[:100]] > cut + 1e-5
+    assert set(ref_order[:100][clear]).issubset(set(top.tolist()))
+    masks = {k: np.zeros((n1, n1)) for k in range(3)}
+    ranker.unmask(masks, top)
+    assert len(ranker.possibilities) == len(poss) - 100 and sum(m.sum() for m in masks.values()) <= 100
+    assert num_to_unmask(1000, 0) == 10 and num_to_unmask(1000, 3) == 40 and num_to_unmask(1000, 7) == 360
+    eng.close()
