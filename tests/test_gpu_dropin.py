@@ -338,7 +338,7 @@ def test_greedy_candidate_ranking_on_device():
     order = ranker.ranked_possibilities()
     assert sorted(order.tolist()) == list(range(len(poss)))
     got = ref_scores[order]
-    assert np.all(np.diff(got) <= 1e-6)  # descending, up to the rounding between the two score paths
+    assert np.all(np.diff(got) <= 3e-6)  # descending, up to the rounding between the two score paths
     top = ranker.get_new_sample_idxs(100)
     assert np.array_equal(top, order[:100])
     # the same set as the reference's argsort, away from near-ties at the cut
