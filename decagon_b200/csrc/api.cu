@@ -737,17 +737,6 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step, StepDep
     join_lanes(g, true);  // lane 1 starts after everything queued so far (previous step's Adam, parameter uploads)
     if (drop) {
         const uint32_t thr = dropout_threshold(rate);
-        for (auto &G : g->groups) {
-            PhaseScope ph(g, "mask", -1, G.lane);
-            cudaStream_t s = lane_stream(g, G.lane);
-            launch_gen_mask(G.mask1, G.mask1_words, G.feat_nnz, 0, G.rel_ids, kStreamDropout1, step, seed, thr, s);
-            g->launches++;
-            // the layer-2 keep words of every group are drawn on a third, low-priority stream: integer ALU work that
-            // runs beside lane 1's L2-bound layer-1 SpMMs; the first staged kernel and every projection wait for it
-            if (g->two_lanes) continue;
-            launch_gen_mask(G.mask2, G.mask2_words, (long long)G.n_j * g->d1, G.n_j * P1, G.rel_ids, kStreamDropout2, step, seed, thr, s);
-            g->launches++;
-        }
         if (g->two_lanes) {
             CUDA_CHECK(cudaEventRecord(g->mask_go, g->stream));  // after the join: last step's readers of mask2 are done
             CUDA_CHECK(cudaStreamWaitEvent(g->stream3, g->mask_go, 0));
@@ -759,6 +748,33 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step, StepDep
                     g->launches++;
                 }
             CUDA_CHECK(cudaEventRecord(g->mask_done, g->stream3));
+        }
+        // layer-1 keep bits of every group: one launch per batch of groups on lane 0 (lane 1 continues behind the join
+        // below); layer-2 keep words: see further down
+        {
+            PhaseScope ph(g, "mask", -1, 0);
+            MaskBatch mb = {};
+            auto flush = [&]() {
+                launch_gen_mask_multi(mb, kStreamDropout1, step, seed, thr, g->stream);
+                if (mb.n) g->launches++;
+                mb.n = 0;
+            };
+            for (auto &G : g->groups) {
+                mb.words[mb.n] = G.mask1, mb.n_words[mb.n] = G.mask1_words, mb.bits_per_rel[mb.n] = G.feat_nnz, mb.rel_ids[mb.n] = G.rel_ids;
+                if (++mb.n == kMaxMaskBatch) flush();
+            }
+            flush();
+        }
+        if (g->two_lanes) {
+            Dep d;
+            produced(g, d, 0);
+            consume(g, d, 1);
+        } else {
+            for (auto &G : g->groups) {
+                launch_gen_mask(G.mask2, G.mask2_words, (long long)G.n_j * g->d1, G.n_j * P1, G.rel_ids, kStreamDropout2, step, seed, thr,
+                                g->stream);
+                g->launches++;
+            }
         }
     }
     bool mask_waited[2] = {!(drop && g->two_lanes), !(drop && g->two_lanes)};

@@ -10,11 +10,14 @@
 //   dh      : B = [W2_hi ; W2_lo] (N = 2 D1), A = G2 hi, lo;                         t[m]  = D[m] + D[D1 + m]
 //   dw2     : A = [Hm_hi ; Hm_lo] (M = 128, lo rows at 64), B = [G2_hi | G2_lo] (N = 64): one MMA per k-step;
 //             dW2[m][n] = D[m][n] + D[m][32 + n] + D[64 + m][n] + D[64 + m][32 + n]
-// Operand tiles (K-major, SWIZZLE_128B) are written by the threads: the dropout mask differs per relation, so the
-// masked operand cannot come from a TMA copy of H.  Thread = one row of the 128-row tile; its H row lives in
-// registers for the CTA's life (project), its dH sums live in registers (dh), the dW2 accumulator lives in TMEM
-// across the row tiles of a relation (dw2).  CTAs are sequential inside (build -> MMA -> read back); two CTAs per SM
-// overlap their phases.  hidden1 is 32 or 64 here (128 stays on the CUDA-core kernels of dense.cu), hidden2 = 32.
+// Operand tiles are written by the threads: the dropout mask differs per relation, so the masked operand cannot come
+// from a TMA copy of H.  Layouts: K-major SWIZZLE_128B where the matrix lies K-contiguous in memory (project A, dh A
+// and B), MN-major SWIZZLE_128B_BASE32B where it lies M/N-contiguous (project B = W2, dw2 A = Hm^T and B = G2^T; see
+// tc_common.cuh and tools/umma_probe.cu), tensor memory for the A operand of project at hidden1 = 64
+// (project_ts_kernel).  project: the thread's H row lives in registers for the CTA's life; dh: the dH sums live in
+// registers; dw2: the accumulator lives in TMEM across the row tiles of a relation.  Global loads are coalesced and one
+// tile ahead.  CTAs are sequential inside (write operands -> MMA -> read back); two CTAs per SM overlap their
+// phases.  hidden1 is 32 or 64 here (128 stays on the CUDA-core kernels of dense.cu), hidden2 = 32.
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -55,9 +58,6 @@ __device__ __forceinline__ void slot_range(int slot, int n_slots, int K, int &k_
     k_end = (int)((long long)(slot + 1) * K / n_slots);
 }
 
-struct TcSetup {
-    uint32_t tmem;
-};
 // TMEM allocation + mbarrier, common prologue
 template <uint32_t COLS>
 __device__ __forceinline__ uint32_t tc_prologue(uint32_t *tmem_slot, uint64_t *bar, const void *smem) {

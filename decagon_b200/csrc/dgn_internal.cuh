@@ -247,6 +247,14 @@ bool staged_supported(int n_i, int n_j, int K);
 void launch_node_epilogue(const EpiArgs &a, int P, cudaStream_t s);
 void launch_l2norm_bwd(const L2BwdArgs &a, int P, cudaStream_t s);
 void launch_relu_bwd(const ReluBwdArgs &a, int P, cudaStream_t s);
+constexpr int kMaxMaskBatch = 8;
+struct MaskBatch {  // layer-1 keep bits of up to kMaxMaskBatch groups, one launch
+    int n;
+    uint32_t *words[kMaxMaskBatch];
+    long long n_words[kMaxMaskBatch], bits_per_rel[kMaxMaskBatch];
+    const int *rel_ids[kMaxMaskBatch];
+};
+void launch_gen_mask_multi(const MaskBatch &mb, uint32_t stream_id, uint32_t step, uint64_t seed, uint32_t threshold, cudaStream_t s);
 void launch_gen_mask(uint32_t *words, long long n_words, long long bits_per_rel, int words_per_rel_or_0, const int *rel_ids,
                      uint32_t stream_id, uint32_t step, uint64_t seed, uint32_t threshold, cudaStream_t s);
 int dense_row_block(int D1, int which);

@@ -192,11 +192,9 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const ReluBwdArgs a) {
 // stream: word (e & 3) of Philox(counter = (e >> 2, relation, stream, step), key = seed).
 // words_per_rel == 0: relations are packed back to back at bit granularity (layer 1, bit index
 // = rel * bits_per_rel + e); otherwise each relation owns words_per_rel whole words (layer 2).
-__global__ void gen_mask_kernel(uint32_t *__restrict__ words, long long n_words, long long bits_per_rel,
-                                int words_per_rel, const int *__restrict__ rel_ids, uint32_t stream_id, uint32_t step, uint32_t seed_lo,
-                                uint32_t seed_hi, uint32_t threshold, long long total_bits) {
-    const long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (w >= n_words) return;
+__device__ __forceinline__ void mask_word(long long w, uint32_t *__restrict__ words, long long bits_per_rel, int words_per_rel,
+                                          const int *__restrict__ rel_ids, uint32_t stream_id, uint32_t step, uint32_t seed_lo,
+                                          uint32_t seed_hi, uint32_t threshold, long long total_bits) {
     uint32_t out = 0;
     const uint2 key = make_uint2(seed_lo, seed_hi);
     if (words_per_rel > 0) {
@@ -217,22 +215,37 @@ __global__ void gen_mask_kernel(uint32_t *__restrict__ words, long long n_words,
         words[w] = out;
         return;
     }
-    long long cached_rel = -1, cached_ctr = -1;
+    // packed relations: walk the 32 bits of the word, one division per word instead of two per bit
+    long long rel = (w * 32) / bits_per_rel, e = (w * 32) % bits_per_rel;
+    long long cached_ctr = -1;
     uint4 rnd = make_uint4(0, 0, 0, 0);
+    uint32_t rid = (uint32_t)rel_ids[rel];
     for (int b = 0; b < 32; ++b) {
-        const long long bit = w * 32 + b;
-        if (bit >= total_bits) break;
-        const long long rel = bit / bits_per_rel, e = bit % bits_per_rel;
+        if (w * 32 + b >= total_bits) break;
         const long long ctr = e >> 2;
-        if (rel != cached_rel || ctr != cached_ctr) {
-            rnd = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)rel_ids[rel], stream_id, step), key);
-            cached_rel = rel;
+        if (ctr != cached_ctr) {
+            rnd = philox4x32_10(make_uint4((uint32_t)ctr, rid, stream_id, step), key);
             cached_ctr = ctr;
         }
         const uint32_t u = (e & 3) == 0 ? rnd.x : (e & 3) == 1 ? rnd.y : (e & 3) == 2 ? rnd.z : rnd.w;
         if (u >= threshold) out |= 1u << b;
+        if (++e == bits_per_rel) {
+            e = 0, ++rel, cached_ctr = -1;
+            rid = (uint32_t)rel_ids[rel];  // rel_ids carries one spare entry past the last relation
+        }
     }
     words[w] = out;
+}
+
+// Grid-stride: the grid is capped at a few CTAs per SM so that the kernel (integer ALU bound) leaves thread and
+// register slots to the L2-bound gather kernels of the other stream lane that run beside it.
+__global__ void __launch_bounds__(256) gen_mask_kernel(uint32_t *__restrict__ words, long long n_words, long long bits_per_rel,
+                                                       int words_per_rel, const int *__restrict__ rel_ids, uint32_t stream_id,
+                                                       uint32_t step, uint32_t seed_lo, uint32_t seed_hi, uint32_t threshold,
+                                                       long long total_bits) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < n_words; w += stride)
+        mask_word(w, words, bits_per_rel, words_per_rel, rel_ids, stream_id, step, seed_lo, seed_hi, threshold, total_bits);
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(float *__restrict__ p, const float *__restrict__ g,
@@ -349,11 +362,30 @@ void launch_signal_wait(uint32_t *const *peer_flags_dev, uint32_t *my_flags, int
     CUDA_CHECK(cudaGetLastError());
 }
 
+// layer-1 keep bits (packed mode) of several groups in one launch: blockIdx.y = group
+__global__ void __launch_bounds__(256) gen_mask_multi_kernel(const MaskBatch mb, uint32_t stream_id, uint32_t step, uint32_t seed_lo,
+                                                             uint32_t seed_hi, uint32_t threshold) {
+    const int q = blockIdx.y;
+    const long long n_words = mb.n_words[q], stride = (long long)gridDim.x * blockDim.x;
+    for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < n_words; w += stride)
+        mask_word(w, mb.words[q], mb.bits_per_rel[q], 0, mb.rel_ids[q], stream_id, step, seed_lo, seed_hi, threshold, n_words * 32);
+}
+
+void launch_gen_mask_multi(const MaskBatch &mb, uint32_t stream_id, uint32_t step, uint64_t seed, uint32_t threshold, cudaStream_t s) {
+    if (mb.n == 0) return;
+    long long most = 0;
+    for (int q = 0; q < mb.n; ++q) most = std::max(most, mb.n_words[q]);
+    if (most == 0) return;
+    dim3 grid((unsigned)std::min<long long>((most + 255) / 256, 148 * 3), (unsigned)mb.n), block(256);
+    gen_mask_multi_kernel<<<grid, block, 0, s>>>(mb, stream_id, step, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), threshold);
+    CUDA_CHECK(cudaGetLastError());
+}
+
 void launch_gen_mask(uint32_t *words, long long n_words, long long bits_per_rel, int words_per_rel, const int *rel_ids,
                      uint32_t stream_id, uint32_t step, uint64_t seed, uint32_t threshold, cudaStream_t s) {
     if (n_words == 0) return;
     const long long total_bits = n_words * 32;  // packed mode: caller rounds the word count up
-    dim3 grid((unsigned)((n_words + 255) / 256)), block(256);
+    dim3 grid((unsigned)std::min<long long>((n_words + 255) / 256, 148 * 3)), block(256);
     gen_mask_kernel<<<grid, block, 0, s>>>(words, n_words, bits_per_rel, words_per_rel, rel_ids, stream_id, step,
                                            (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), threshold,
                                            total_bits);
