@@ -301,3 +301,18 @@ def test_ndarray_io_predict_matches_nppredictor_golden():
         want = gold['pred%d' % k]
         got = ndarray_io.np_predict_edges(Z, D[k], R, edges)
         assert np.abs(got - want[:, 2]).max() <= 2e-6
+
+
+def test_multi_hot_features_and_unmask_schedule():
+    """Host helpers around the widened path: the multi-hot feature generator (shape of the reference's drug features,
+    DecagonPublicDataNodeFeaturesBuilder.py:34-51) and RandomMaskingActiveLearner._updateMask's schedule (:166-171)."""
+    from decagon_b200.active_learning import num_to_unmask
+    x = datasets.multi_hot_features(97, 213, per_row=9, seed=4)
+    assert x.shape == (97, 213) and x.nnz > 97 and set(np.unique(x.data)) == {1.0}
+    assert np.all(np.diff(x.indptr) >= 1)                      # every node has at least one feature
+    assert np.array_equal(x.toarray(), datasets.multi_hot_features(97, 213, per_row=9, seed=4).toarray())
+    inputs = datasets.toy_graph(features={1: datasets.multi_hot_features(400, 150, per_row=6, seed=3)})
+    assert inputs.num_feat == {0: 500, 1: 150} and inputs.nonzero_feat[1] == inputs.feat[1][1].sum()
+    # 1 %, 1 %, 2 %, 4 %, ... of the data set, capped at 100 % in total
+    sizes = [num_to_unmask(10000, i) for i in range(8)]
+    assert sizes == [100, 100, 200, 400, 800, 1600, 3200, 3600] and sum(sizes) == 10000
