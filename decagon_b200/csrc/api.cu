@@ -410,6 +410,7 @@ struct dgn_graph {
     float *decode_scratch = nullptr;
     unsigned *decode_ticket = nullptr;
     int last_B = 0;
+    bool dzq_clean = false;  // the fixed-point dZ accumulators are zero (cleared by the conversion kernel)
     // measurement
     bool timing = false;
     cudaEvent_t timer_start = nullptr, timer_stop = nullptr;
@@ -1761,7 +1762,9 @@ extern "C" int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t
     {
         for (int t = 0; t < g->n_types; ++t) consume(g, deps.Z[t], 0);
         PhaseScope ph(g, "decode");
-        for (auto &T : g->types) CUDA_CHECK(cudaMemsetAsync(T.dZq, 0, panel_floats(1, T.n) * sizeof(long long), s));
+        if (!g->dzq_clean)  // normally left clean by the previous step's conversion kernel
+            for (auto &T : g->types) CUDA_CHECK(cudaMemsetAsync(T.dZq, 0, panel_floats(1, T.n) * sizeof(long long), s));
+        g->dzq_clean = false;
         if (g->n_params > g->dec_off)
             CUDA_CHECK(cudaMemsetAsync(g->grads + g->dec_off, 0, (g->n_params - g->dec_off) * sizeof(float), s));
         DecodeArgs a = {};
@@ -1779,9 +1782,17 @@ extern "C" int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t
         a.scratch = g->decode_scratch, a.ticket = g->decode_ticket;
         launch_decode(a, s);
         g->launches++;
-        for (auto &T : g->types) {
-            launch_fixed_to_float(T.dZq, T.dZ, panel_floats(1, T.n), s);
+        if (g->n_types <= kMaxTypes) {
+            FixedBatch fb = {};
+            for (auto &T : g->types) fb.q[fb.count] = T.dZq, fb.out[fb.count] = T.dZ, fb.n[fb.count] = (size_t)panel_floats(1, T.n), fb.count++;
+            launch_fixed_to_float_clear(fb, s);
             g->launches++;
+            g->dzq_clean = true;
+        } else {
+            for (auto &T : g->types) {
+                launch_fixed_to_float(T.dZq, T.dZ, panel_floats(1, T.n), s);
+                g->launches++;
+            }
         }
         g->last_B = batch_size;
         for (int t = 0; t < g->n_types; ++t) produced(g, deps.dZ[t], 0);

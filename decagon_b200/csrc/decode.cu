@@ -279,6 +279,26 @@ void launch_decode(const DecodeArgs &a, cudaStream_t s) {
     CUDA_CHECK(cudaGetLastError());
 }
 
+// every node type in one launch (blockIdx.y = type); the fixed-point accumulator is cleared on the way out, so the
+// next step needs no memset between its forward and backward passes
+__global__ void fixed_to_float_clear_kernel(const FixedBatch fb) {
+    long long *q = fb.q[blockIdx.y];
+    float *out = fb.out[blockIdx.y];
+    const size_t n = fb.n[blockIdx.y];
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        out[i] = (float)((double)q[i] * (1.0 / 1099511627776.0));
+        q[i] = 0;
+    }
+}
+void launch_fixed_to_float_clear(const FixedBatch &fb, cudaStream_t s) {
+    size_t most = 0;
+    for (int t = 0; t < fb.count; ++t) most = std::max(most, fb.n[t]);
+    if (fb.count == 0 || most == 0) return;
+    dim3 grid((unsigned)std::min<size_t>((most + 255) / 256, 148 * 4), (unsigned)fb.count);
+    fixed_to_float_clear_kernel<<<grid, 256, 0, s>>>(fb);
+    CUDA_CHECK(cudaGetLastError());
+}
+
 void launch_fixed_to_float(const long long *q, float *out, size_t n, cudaStream_t s) {
     if (n == 0) return;
     fixed_to_float_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(q, out, n);

@@ -377,15 +377,15 @@ __global__ void __launch_bounds__(kThreads, 2) dh_tc_kernel(const DenseArgs a) {
         fence_async_smem();
         fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {  // convergent warp, one elected lane issues
             fence_after();
             const uint64_t ahi = umma_desc(smem_u32(Ahi)), alo = umma_desc(smem_u32(Alo)), b = umma_desc(smem_u32(Bs));
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-                mma_tf32(tmem, ahi + 2 * ks, b + 2 * ks, kIdesc, ks != 0);
-                mma_tf32(tmem, alo + 2 * ks, b + 2 * ks, kIdesc, 1);
+                mma_tf32_elect(tmem, ahi + 2 * ks, b + 2 * ks, kIdesc, ks != 0);
+                mma_tf32_elect(tmem, alo + 2 * ks, b + 2 * ks, kIdesc, 1);
             }
-            mma_commit(&mma_done);
+            mma_commit_elect(&mma_done);
         }
         mbar_wait(&mma_done, parity);
         parity ^= 1;
@@ -541,14 +541,14 @@ __global__ void __launch_bounds__(kThreads, 2) dw2_tc_kernel(const DenseArgs a, 
         fence_async_smem();
         fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {  // convergent warp, one elected lane issues
             fence_after();
 #pragma unroll
             for (int ks = 0; ks < 16; ++ks) {
                 const uint64_t ad = umma_desc_mn(smem_u32(As + ks * 4096), 1024), bd = umma_desc_mn(smem_u32(Bs + ks * 2048), 1024);
-                mma_tf32(tmem, ad, bd, kIdesc, !first_tile || ks != 0);
+                mma_tf32_elect(tmem, ad, bd, kIdesc, !first_tile || ks != 0);
             }
-            mma_commit(&mma_done);
+            mma_commit_elect(&mma_done);
         }
         pending = true;
     }

@@ -269,6 +269,14 @@ void launch_project_tc(const DenseArgs &a, int D1, cudaStream_t s);
 void launch_dw2_tc(const DenseArgs &a, int D1, cudaStream_t s);
 void launch_dh_tc(const DenseArgs &a, int D1, cudaStream_t s);
 void launch_decode(const DecodeArgs &a, cudaStream_t s);
+constexpr int kMaxTypes = 8;
+struct FixedBatch {
+    int count;
+    long long *q[kMaxTypes];
+    float *out[kMaxTypes];
+    size_t n[kMaxTypes];
+};
+void launch_fixed_to_float_clear(const FixedBatch &fb, cudaStream_t s);
 void launch_fixed_to_float(const long long *q, float *out, size_t n, cudaStream_t s);
 void launch_predict(const PredictArgs &a, cudaStream_t s);
 void launch_predict_tc(const PredictArgs &a, int n_sm, cudaStream_t s);  // tcgen05, 3 x TF32 (predict_tc.cu)

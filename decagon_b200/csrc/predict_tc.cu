@@ -142,17 +142,17 @@ __global__ void __launch_bounds__(kThreads, 2) predict_tc_kernel(const PredictAr
             fence_async_smem();
             fence_before();
             __syncthreads();
-            if (tid == 0) {
+            if (warp == 0) {  // convergent warp, one elected lane issues
                 fence_after();
                 const uint64_t ahi = umma_desc(smem_u32(Ahi)), alo = umma_desc(smem_u32(Alo));
                 const uint64_t bhi = umma_desc(smem_u32(Bhi)), blo = umma_desc(smem_u32(Blo));
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {  // K = 8 tf32 = 32 bytes per instruction: + 2 in the encoded address
-                    mma_tf32(tmem, ahi + 2 * ks, bhi + 2 * ks, idesc, ks > 0);
-                    mma_tf32(tmem, alo + 2 * ks, bhi + 2 * ks, idesc, 1);
-                    mma_tf32(tmem, ahi + 2 * ks, blo + 2 * ks, idesc, 1);
+                    mma_tf32_elect(tmem, ahi + 2 * ks, bhi + 2 * ks, idesc, ks > 0);
+                    mma_tf32_elect(tmem, alo + 2 * ks, bhi + 2 * ks, idesc, 1);
+                    mma_tf32_elect(tmem, ahi + 2 * ks, blo + 2 * ks, idesc, 1);
                 }
-                mma_commit(&mma_done);
+                mma_commit_elect(&mma_done);
             }
             mbar_wait(&mma_done, parity);
             parity ^= 1;
