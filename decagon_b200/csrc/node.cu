@@ -6,6 +6,8 @@
 //   relu_bwd_kernel      -- ordered sum of the dH partials + ReLU mask
 //   gen_mask_kernel      -- Philox4x32-10 dropout keep-bits (layers.py:23-31, :112)
 //   adam_kernel          -- TF-1.8 ApplyAdam (optimizer.py:111-113)
+#include <stdlib.h>
+
 #include <algorithm>
 #include <type_traits>
 
@@ -385,7 +387,12 @@ void launch_gen_mask(uint32_t *words, long long n_words, long long bits_per_rel,
                      uint32_t stream_id, uint32_t step, uint64_t seed, uint32_t threshold, cudaStream_t s) {
     if (n_words == 0) return;
     const long long total_bits = n_words * 32;  // packed mode: caller rounds the word count up
-    dim3 grid((unsigned)std::min<long long>((n_words + 255) / 256, 148 * 3)), block(256);
+    static int ctas_per_sm = 0;  // DGN_MASK_CTAS: CTAs per SM the layer-2 mask kernel may occupy (default 3)
+    if (ctas_per_sm == 0) {
+        const char *e = getenv("DGN_MASK_CTAS");
+        ctas_per_sm = e && atoi(e) > 0 ? atoi(e) : 3;
+    }
+    dim3 grid((unsigned)std::min<long long>((n_words + 255) / 256, 148LL * ctas_per_sm)), block(256);
     gen_mask_kernel<<<grid, block, 0, s>>>(words, n_words, bits_per_rel, words_per_rel, rel_ids, stream_id, step,
                                            (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), threshold,
                                            total_bits);
