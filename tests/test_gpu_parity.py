@@ -312,3 +312,36 @@ def test_general_sparse_features(graph_kind):
             for gg in p[name]:
                 assert np.abs(now[name][gg] - p[name][gg]).max() <= 2e-7, (step, name, gg)
     eng.close()
+
+
+@pytest.mark.parametrize('env', [{'DGN_SINGLE_STREAM': '1'}, {'DGN_PROJECT_SS': '1'}, {'DGN_FUSE_ADAM': '0'},
+                                 {'DGN_DISABLE_TSTAGED': '1'}, {'DGN_MASK_CTAS': '1'}])
+def test_alternate_code_paths(env):
+    """The switches that select the non-default kernels / schedules (one stream instead of the lanes + mask stream,
+    the shared-memory projection instead of the tensor-memory one, unfused Adam, gather-path backward) give the
+    same results: forward, gradients and two optimizer steps against the oracle on the staged mini graph."""
+    c = Case(common.mini_poly(n_types=9, seed=77), batch_size=64)
+    os.environ.update(env)
+    try:
+        eng = c.engine()
+        check_forward(c, eng, 0.1, 1)
+        for step, (r, batch) in enumerate(c.batches(2)):
+            check_grads(c, eng, r, batch, 0.1, step, 'hinge')
+        eng.reset_optimizer()
+        p = O.cast_params(eng.get_params(), np.float64)
+        adam = O.AdamTF1(p, lr=1e-3)
+        for step, (r, batch) in enumerate(c.batches(2)):
+            g, k = c.graph.flat[r]
+            negs = O.sample_negatives(c.thresholds(r), len(batch), r, step, SEED)
+            masks = O.masks_for(c.graph, 0.1, step, SEED)
+            _, _, _, grads, _ = O.train_step_grads(c.graph, p, g, k, batch, negs, 0.1, masks, 'hinge')
+            adam.apply(p, grads)
+            eng.train_step(r, batch, negatives=negs, seed=SEED, step=step, dropout=0.1, apply_update=True)
+        now = eng.get_params()
+        for name in ('W2', 'R', 'D'):
+            for gg in now[name]:
+                assert rel_err(now[name][gg], p[name][gg]) <= 1e-4, (env, name, gg)
+        eng.close()
+    finally:
+        for k in env:
+            del os.environ[k]
