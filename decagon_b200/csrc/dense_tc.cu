@@ -502,13 +502,22 @@ __global__ void __launch_bounds__(kThreads, 2) dw2_tc_kernel(const DenseArgs a, 
     uint32_t parity = 0;
     bool pending = false, prev_closed = false, first = true;
     int prev_k = 0, prev_chunk = 0;
+#ifdef DGN_TC_PROFILE
+    long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_t = clock64();
+    long long prof_tiles = 0;
+#endif
     while (u < u_end) {
+#ifdef DGN_TC_PROFILE
+        ++prof_tiles;
+#endif
         if (pending) {  // the previous tile's MMAs still read the operand tiles
             mbar_wait(&mma_done, parity);
             parity ^= 1;
             fence_after();
             if (prev_closed) unit_epilogue(prev_k, prev_chunk);
         }
+        TC_CLK(0);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int kblk = 2 * i + (lrow >> 3);  // (lrow + 16 i) >> 3
@@ -537,10 +546,13 @@ __global__ void __launch_bounds__(kThreads, 2) dw2_tc_kernel(const DenseArgs a, 
             first = true;
             if (u < u_end) open_unit();
         }
+        TC_CLK(1);
         if (u < u_end) fetch(k, t);
+        TC_CLK(2);
         fence_async_smem();
         fence_before();
         __syncthreads();
+        TC_CLK(3);
         if (warp == 0) {  // convergent warp, one elected lane issues
             fence_after();
 #pragma unroll
@@ -550,8 +562,15 @@ __global__ void __launch_bounds__(kThreads, 2) dw2_tc_kernel(const DenseArgs a, 
             }
             mma_commit_elect(&mma_done);
         }
+        TC_CLK(4);
         pending = true;
     }
+#ifdef DGN_TC_PROFILE
+    if (tid == 0) {
+        for (int i = 0; i < 5; ++i) atomicAdd(&g_tc_prof[i], (unsigned long long)prof_acc[i]);
+        atomicAdd(&g_tc_prof[6], (unsigned long long)prof_tiles);
+    }
+#endif
     if (pending) {
         mbar_wait(&mma_done, parity);
         fence_after();
@@ -636,6 +655,18 @@ void launch_dw2_tc(const DenseArgs &a, int D1, cudaStream_t s) {
     if (D1 == 64) {
         set_smem(dw2_tc_kernel<64>, bytes);
         dw2_tc_kernel<64><<<grid, kThreads, bytes, s>>>(a, n_tiles);
+#ifdef DGN_TC_PROFILE
+        if (a.K > 100) {
+            unsigned long long h[8];
+            cudaStreamSynchronize(s);
+            cudaMemcpyFromSymbol(h, g_tc_prof, sizeof(h));
+            const double it = (double)h[6];
+            fprintf(stderr, "dw2_tc phases (thread 0, cycles per tile over %.0f tiles): wait prev MMA (+ unit epilogue) %.0f  operand writes %.0f  "
+                            "next loads issued %.0f  fence+bar %.0f  issue %.0f\n", it, h[0] / it, h[1] / it, h[2] / it, h[3] / it, h[4] / it);
+            unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            cudaMemcpyToSymbol(g_tc_prof, z, sizeof(z));
+        }
+#endif
     } else {
         set_smem(dw2_tc_kernel<32>, bytes);
         dw2_tc_kernel<32><<<grid, kThreads, bytes, s>>>(a, n_tiles);
