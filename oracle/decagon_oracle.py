@@ -13,7 +13,7 @@ What it restates (numpy, float64 as the arbiter or float32 as the reference-prec
 * hinge / xent loss   ``optimizer.py:116-127``
 * reverse-mode gradients of all of the above (what ``AdamOptimizer.minimize`` differentiates,
   ``optimizer.py:111-113``), hand-derived and cross-checked against torch
-  autograd in ``tests/test_oracle.py``
+  autograd in ``tests/test_host.py::test_oracle_backward_matches_autograd``
 * TF-1.8 ``ApplyAdam`` update (``requirements.txt:22``; TF is a third-party dependency that is
   not under /root/reference and cannot be installed here -- its published semantics are restated:
   ``alpha = lr*sqrt(1-b2^t)/(1-b1^t); m += (g-m)(1-b1); v += (g*g-v)(1-b2);

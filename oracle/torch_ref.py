@@ -7,7 +7,7 @@ hinge loss, autograd for the backward pass and the TF-1.8 Adam formula:
 ``decagon/deep/layers.py:85-118``, ``model.py:64-137``, ``optimizer.py:29-127``.
 
 Two uses:
-* ``tests/test_oracle.py`` -- autograd gradients as an independent check of the hand-derived
+* ``tests/test_host.py::test_oracle_backward_matches_autograd`` -- autograd gradients as an independent check of the hand-derived
   backward pass in ``decagon_oracle.py`` (float64);
 * ``bench.py`` -- the ``cpu_baseline`` / ``--impl reference`` timing ("kind": "port"): TensorFlow
   1.8 cannot be installed here, so this is the stand-in for the reference's CPU path, float32,
