@@ -85,13 +85,16 @@ def next_batch(it):
     return int(fd['batch_edge_type_idx']), np.ascontiguousarray(fd['batch'], dtype=np.int32)
 
 
-def algorithmic_bytes(inputs, it, hidden1, hidden2):
+def algorithmic_bytes(inputs, it, hidden1, hidden2, is_local=None):
     """fp32 values, int32 indices, CSR, dense operand counted once per relation,
-    no cache credit.  Returns {phase: bytes per launch}."""
+    no cache credit.  Returns {phase: bytes per launch}.  is_local(g, k): the relations THIS rank's launch
+    processes (multi-GPU: the bytes of one rank's kernel, not of the whole graph)."""
     out = {}
-    for gi, (g, K) in enumerate(inputs.edge_types.items()):
+    for gi, (g, K_all) in enumerate(inputs.edge_types.items()):
         n_i, n_j = inputs.n_nodes[g[0]], inputs.n_nodes[g[1]]
-        nnz = sum(len(it.adj_train[g][k][1]) for k in range(K))
+        mine = [k for k in range(K_all) if is_local is None or is_local(g, k)]
+        K = len(mine)
+        nnz = sum(len(it.adj_train[g][k][1]) for k in mine)
         csr = nnz * 8 + K * (n_i + 1) * 4
         csr_t = nnz * 8 + K * (n_j + 1) * 4
         out['spmm_fwd1/g%d' % gi] = csr + K * n_j * hidden1 * 4 + n_i * hidden1 * 4
@@ -99,6 +102,17 @@ def algorithmic_bytes(inputs, it, hidden1, hidden2):
         out['spmm_bwd2/g%d' % gi] = csr_t + n_i * hidden2 * 4 + K * hidden1 * hidden2 * 4 + n_j * hidden1 * 4
         out['spmm_bwd1/g%d' % gi] = csr_t + n_i * hidden1 * 4 + K * n_j * hidden1 * 4
     return out
+
+
+def load_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the newest committed
+    ncu --set full capture (profiles/rNN_traffic.json; one GPU, polypharmacy shape)."""
+    for name in ('r02_traffic.json', 'r01_traffic.json'):
+        try:
+            return json.load(open(os.path.join(ROOT, 'profiles', name)))
+        except Exception:
+            continue
+    return {}
 
 
 class ClockSampler(threading.Thread):
@@ -172,12 +186,13 @@ def run_reference(args):
         return
     inputs, it = build_workload(args.config, args.scale)
     params = glorot_params(inputs, HYPER['hidden1'], HYPER['hidden2'])
-    sec, n_timed, sample = cpu_port_steps(inputs, it, params, args.steps, 1, args.reference_budget)
+    n_warm = max(args.warmup, 1)
+    sec, n_timed, sample = cpu_port_steps(inputs, it, params, args.steps, n_warm, args.reference_budget)
     spe = steps_per_epoch(it)
     value = 1.0 / sec / spe
     line = {
         'impl': 'reference', 'metric': 'train_epochs_per_s', 'value': value, 'unit': 'epochs/s', 'n_gpus': args.gpus,
-        'steps': n_timed, 'warmup': 1, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
+        'steps': n_timed, 'warmup': n_warm, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
         'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'steps_per_s': 1.0 / sec, 'steps_per_epoch': spe,
         'config': workload_config(args, inputs),
@@ -196,10 +211,68 @@ def workload_config(args, inputs):
             'scale': args.scale, 'l2': 'per-step working set (>4 GB) exceeds the 126 MB L2; no explicit flush'}
 
 
+def construct_placeholders(edge_types):
+    """DecagonDataSet._getPlaceholdersDict (DecagonDataSet.py:84-120) with tf -> decagon_b200.tf_compat."""
+    from decagon_b200 import tf_compat as tf
+    ph = {
+        'batch': tf.placeholder(tf.int32, name='batch'),
+        'batch_edge_type_idx': tf.placeholder(tf.int32, shape=(), name='batch_edge_type_idx'),
+        'batch_row_edge_type': tf.placeholder(tf.int32, shape=(), name='batch_row_edge_type'),
+        'batch_col_edge_type': tf.placeholder(tf.int32, shape=(), name='batch_col_edge_type'),
+        'degrees': tf.placeholder(tf.int32),
+        'dropout': tf.placeholder_with_default(0., shape=()),
+    }
+    ph.update({'adj_mats_%d,%d,%d' % (i, j, k): tf.sparse_placeholder(tf.float32)
+               for i, j in edge_types for k in range(edge_types[i, j])})
+    ph.update({'feat_%d' % i: tf.sparse_placeholder(tf.float32) for i, _ in edge_types})
+    return ph
+
+
+def build_trainable(inputs, it):
+    """DecagonTrainableBuilder.build (DecagonTrainableBuilder.py:56-118) against the drop-in classes."""
+    from decagon_b200 import tf_compat as tf
+    from decagon_b200.deep import inits
+    from decagon_b200.deep.model import DecagonModel
+    from decagon_b200.deep.optimizer import DecagonOptimizer
+    tf.FLAGS.hidden1, tf.FLAGS.hidden2, tf.FLAGS.learning_rate = HYPER['hidden1'], HYPER['hidden2'], HYPER['lr']
+    placeholders = construct_placeholders(inputs.edge_types)
+    inits.set_seed(1)
+    model = DecagonModel(placeholders, inputs.num_feat, inputs.nonzero_feat, inputs.edge_types, inputs.edge_type2decoder)
+    with tf.name_scope('optimizer'):
+        opt = DecagonOptimizer(model.embeddings, model.latent_inters, model.latent_varies, inputs.degrees,
+                               inputs.edge_types, inputs.edge_type2dim, placeholders, margin=HYPER['margin'],
+                               neg_sample_weights=1., batch_size=HYPER['batch_size'])
+    return placeholders, model, opt
+
+
+def model_params(model):
+    """The model's initial variables as the engine's parameter dict."""
+    p = {'W1': {}, 'W2': {}, 'R': {}, 'D': {}}
+    for g, K in model.edge_types.items():
+        p['W1'][g] = np.stack([model.layer1[g].vars['weights_%d' % k].initial for k in range(K)])
+        p['W2'][g] = np.stack([model.layer2[g].vars['weights_%d' % k].initial for k in range(K)])
+        dec = model.edge_type2decoder[g]
+        if dec.kind == 'dedicom':
+            p['R'][g] = dec.vars['global_interaction'].initial
+            p['D'][g] = np.stack([dec.vars['local_variation_%d' % k].initial for k in range(K)])
+        elif dec.kind in ('distmult', 'bilinear'):
+            p['D'][g] = np.stack([dec.vars['relation_%d' % k].initial for k in range(K)])
+    return p
+
+
+def equivalence_steps(eng, batches, n_types):
+    """Three training steps from the initial parameters, then one forward: (losses, embeddings)."""
+    losses = [float(eng.train_step(r, b, loss='hinge', margin=HYPER['margin'], lr=HYPER['lr'], dropout=HYPER['dropout'],
+                                   seed=SEED, step=i)) for i, (r, b) in enumerate(batches)]
+    eng.forward(0.0, SEED, 0)
+    return losses, [eng.embeddings(t) for t in range(n_types)]
+
+
 def run_ours(args):
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    from decagon_b200 import tf_compat as tf
     from decagon_b200.engine import Engine
 
     dist = None
@@ -213,25 +286,63 @@ def run_ours(args):
 
     inputs, it = build_workload(args.config, args.scale)
     t0 = time.time()
-    eng = Engine(inputs.n_nodes, inputs.num_feat, inputs.edge_types, inputs.edge_type2decoder, HYPER['hidden1'],
-                 HYPER['hidden2'], device=local_rank)
-    if world > 1:
-        eng.comm_init(rank, world)  # relations of the many-relation groups are partitioned over the ranks
-    eng.load_iterator(it, inputs.degrees)
-    if world > 1:
-        eng.connect(dist)           # CUDA IPC handles of the exchange arenas, all-gathered
-    eng.set_params(glorot_params(inputs, HYPER['hidden1'], HYPER['hidden2']))
-    eng.reset_optimizer()
-    log('engine loaded in %.1fs, %d parameters' % (time.time() - t0, eng.n_params()))
-
+    # the reference's own construction sequence: placeholders, model, optimizer, session
+    placeholders, model, opt = build_trainable(inputs, it)
+    sess = tf.Session(seed=SEED, device=local_rank)
     np.random.seed(2)
     it.shuffle()
+    n_types = len(inputs.n_nodes)
+
+    def feed():  # what DecagonTrainer.train builds per step (DecagonTrainer.py:86-93)
+        return it.update_feed_dict(it.next_minibatch_feed_dict(placeholders), HYPER['dropout'], placeholders)
+
+    def as_batch(fd):
+        return int(fd[placeholders['batch_edge_type_idx']]), np.ascontiguousarray(fd[placeholders['batch']], dtype=np.int32)
+
+    eq_batches = [as_batch(feed()) for _ in range(3)]
+    equivalence = None
+    ref_eq = None
+    if world > 1 and not args.no_equivalence:
+        # multi-GPU equivalence: rank 0 alone first runs three steps on an UN-partitioned engine
+        # (no device allocation may happen next to a live partitioned engine that peers wait on)
+        if rank == 0:
+            ref = Engine(inputs.n_nodes, inputs.num_feat, inputs.edge_types, inputs.edge_type2decoder, HYPER['hidden1'],
+                         HYPER['hidden2'], device=local_rank)
+            ref.load_iterator(it, inputs.degrees)
+            ref.set_params(model_params(model))
+            ref.reset_optimizer()
+            ref_eq = equivalence_steps(ref, eq_batches, n_types)
+            ref.close()
+            del ref
+        dist.barrier()
+
+    sess.run(tf.global_variables_initializer())
+    sess.run(model.embeddings[1], feed_dict=feed())  # builds, partitions (world > 1), uploads and initialises the engine
+    eng = model.engine
+    log('engine loaded in %.1fs, %d parameters' % (time.time() - t0, eng.n_params()))
+
+    if world > 1 and not args.no_equivalence:
+        import hashlib
+        losses_p, Z_p = equivalence_steps(eng, eq_batches, n_types)
+        digests = [None] * world
+        dist.all_gather_object(digests, hashlib.sha256(b''.join(z.tobytes() for z in Z_p)).hexdigest())
+        if rank == 0:
+            rel = lambda a, b: float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max() / np.abs(b).max())
+            equivalence = {
+                'what': '3 training steps + 1 forward from identical parameters: %d-rank partitioned engine vs the '
+                        'un-partitioned engine on rank 0' % world,
+                'loss_first_step_rel_err': abs(losses_p[0] - ref_eq[0][0]) / abs(ref_eq[0][0]),
+                'loss_rel_err_max': max(abs(a - b) / abs(b) for a, b in zip(losses_p, ref_eq[0])),
+                'embeddings_rel_err_max': max(rel(a, b) for a, b in zip(Z_p, ref_eq[1])),
+                'ranks_bit_identical': all(d == digests[0] for d in digests),
+                'tolerance': 1e-5, 'losses': losses_p, 'losses_one_gpu': ref_eq[0]}
+        sess.run(tf.global_variables_initializer())  # back to the initial parameters and zeroed Adam slots
+
+    fetches = [opt.opt_op, opt.cost, opt.batch_edge_type_idx]
     kw = dict(loss='hinge', margin=HYPER['margin'], lr=HYPER['lr'], dropout=HYPER['dropout'], seed=SEED)
-    step = 0
     for _ in range(max(args.warmup, 3)):
-        r, batch = next_batch(it)
-        eng.train_step(r, batch, step=step, **kw)
-        step += 1
+        sess.run(fetches, feed_dict=feed())
+    step = 1000000  # the engine-level legs below use their own step numbers (dropout / sampler stream keys)
 
     def barrier():
         eng.sync()
@@ -243,7 +354,7 @@ def run_ours(args):
 
     # (1) device-resident throughput: graph, parameters and optimizer state live in HBM; the only
     # per-step input is the 4 KB batch index block; CUDA events on the library's stream
-    batches = [next_batch(it) for _ in range(args.steps)]
+    batches = [as_batch(feed()) for _ in range(args.steps)]
     barrier()
     eng.timing_reset()
     eng.timer_start()
@@ -254,15 +365,15 @@ def run_ours(args):
     launches = eng.launch_count()
     barrier()
 
-    # (2) end to end through the public call with host buffers: host iterator, H2D of the batch,
-    # the step, D2H of the loss, every step
+    # (2) end to end through the drop-in boundary, exactly the reference trainer's loop body
+    # (DecagonTrainer.py:86-100): iterator -> feed dict with all 1932 adjacency entries -> Session.run with host
+    # buffers (H2D of the batch inside), the step, D2H of the loss, every step
     barrier()
     t0 = time.perf_counter()
     losses = []
     for _ in range(args.steps):
-        r, batch = next_batch(it)
-        losses.append(eng.train_step(r, batch, step=step, want_loss=True, **kw))
-        step += 1
+        outs = sess.run(fetches, feed_dict=feed())
+        losses.append(outs[1])
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.summary()
@@ -275,7 +386,9 @@ def run_ours(args):
         eng.train_step(r, batch, step=step, want_loss=False, **kw)
         step += 1
     eng.sync()
-    alg = algorithmic_bytes(inputs, it, HYPER['hidden1'], HYPER['hidden2'])
+    flat_index = {gk: r for r, gk in enumerate(eng.flat)}
+    alg = algorithmic_bytes(inputs, it, HYPER['hidden1'], HYPER['hidden2'],
+                            (lambda g, k: eng.relation_owner(flat_index[(g, k)]) in (-1, rank)) if world > 1 else None)
     phases = {}
     names = list(alg) + ['project', 'dw2', 'dh', 'mask', 'epilogue', 'decode', 'adam']
     names += ['%s/g%d' % (n, gi) for n in ('project', 'dw2', 'dh') for gi in range(len(inputs.edge_types))]
@@ -308,7 +421,7 @@ def run_ours(args):
     traffic = None  # DRAM bytes per launch of that kernel from the committed ncu --set full capture (1 GPU, poly shape)
     try:
         if world == 1 and args.config == 'poly' and args.scale == 1:
-            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json'))).get(top)
+            traffic = load_traffic().get(top)
     except Exception:
         pass
     spe = steps_per_epoch(it)
@@ -322,7 +435,9 @@ def run_ours(args):
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'steps_per_s': sps, 'steps_per_epoch': spe,
         'config': workload_config(args, inputs),
         'clocks': clocks,
-        'e2e': {'value': e2e_sps / spe, 'unit': 'epochs/s', 'steps_per_s': e2e_sps,
+        'e2e': {'value': e2e_sps / spe, 'unit': 'epochs/s', 'steps_per_s': e2e_sps, 'ms_per_step': 1e3 / e2e_sps,
+                'through': 'tf_compat.Session.run([opt.opt_op, opt.cost, opt.batch_edge_type_idx], '
+                           'iterator.update_feed_dict(iterator.next_minibatch_feed_dict(...)))',
                 'h2d_bytes_per_step': HYPER['batch_size'] * 2 * 4, 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches),
         'roofline': {'bound': 'hbm', 'kernel': top, 'achieved': spmm[top]['gbs'], 'peak': peak, 'unit': 'GB/s',
@@ -331,6 +446,10 @@ def run_ours(args):
         'kernels': phases,
         'loss_first_last': [float(losses[0]), float(losses[-1])],
     }
+    if world > 1:
+        line['roofline']['per_rank'] = 'algorithmic bytes and time of ONE rank\'s launch (its own relations of the partitioned group)'
+    if equivalence is not None:
+        line['equivalence'] = equivalence
     # The longest kernel of the step is the layer-1 backward SpMM of the many-relation group with the TF1 Adam of its
     # weights fused in (the gradient never reaches HBM).  SURVEY.md 8(d): transposed CSR + dS + Adam state, "2.1 GB if
     # fused into the dW epilogue" = read p, m, v and write p, m, v: 6 x 4 B per parameter instead of the dW1 write.
@@ -346,8 +465,7 @@ def run_ours(args):
                 'bound': 'hbm', 'kernel': bw + ' (spmm_tstaged_kernel<2>, Adam fused)', 'algorithmic_bytes': fused,
                 'ms': phases[bw]['ms_per_step'], 'achieved': fused / phases[bw]['ms_per_step'] / 1e6, 'peak': peak,
                 'unit': 'GB/s', 'frac': fused / phases[bw]['ms_per_step'] / 1e6 / peak,
-                'traffic': (json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json'))).get(bw)
-                            if args.config == 'poly' and args.scale == 1 else None)}
+                'traffic': load_traffic().get(bw) if args.config == 'poly' and args.scale == 1 else None}
     except Exception:
         pass
     if world == 1 and args.config == 'poly' and args.scale == 1:
@@ -392,6 +510,7 @@ def main():
     ap.add_argument('--scale', type=int, default=1)
     ap.add_argument('--reference-budget', type=float, default=150.0, help='seconds of timed CPU steps')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-equivalence', action='store_true', help='skip the N-GPU vs 1-GPU equivalence steps (N > 1)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

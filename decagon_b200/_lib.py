@@ -52,6 +52,7 @@ SIGNATURES = {
                                       ctypes.c_uint32, ctypes.c_int, c_f32p]),
     'dgn_last_batch_outputs': (ctypes.c_int, [c_graph, c_f32p, c_f32p, c_i64p, ctypes.c_int32]),
     'dgn_grads_get': (ctypes.c_int, [c_graph, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f32p, ctypes.c_int64]),
+    'dgn_keep_gradients': (ctypes.c_int, [c_graph, ctypes.c_int]),
     'dgn_predict_all_pairs': (ctypes.c_int, [c_graph, ctypes.c_int, c_f32p]),
     'dgn_predict_relations_dev': (ctypes.c_int, [c_graph, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     'dgn_predict_edges': (ctypes.c_int, [c_graph, ctypes.c_int, c_i32p, ctypes.c_int32, ctypes.c_int, c_f32p]),

@@ -340,6 +340,7 @@ struct Group {
     SlotTable slots1, slots2;
     int staged_version = 3;      // 2: spmm_staged_kernel, 3: spmm_staged3_kernel (position order, mbarrier pipeline)
     bool tstaged = false;        // backward products through spmm_tstaged_kernel
+    bool w1_grad_stale = false;  // the last step fused Adam into the gradient kernel: grads of W1 were never written
     TaskCsr task_fwd, task_bwd;
     SlotTable slots_bwd;
     int *wstart1 = nullptr, *wstart2 = nullptr, *wstart_bwd = nullptr;
@@ -392,6 +393,7 @@ struct dgn_graph {
     int n_exchanges = 0;
     bool two_lanes = true;
     bool fuse_adam = true;  // Adam of the layer-1 weights inside the kernel that produces their gradient
+    bool keep_grads = false;  // dgn_keep_gradients: every gradient is materialised (no fused Adam)
     std::vector<cudaEvent_t> dep_events;  // pool, reused every step
     size_t dep_next = 0;
     // parameters
@@ -918,6 +920,12 @@ struct AdamStep {  // valid (alpha != 0) when the update may be fused into the k
     float alpha = 0.f, omb1 = 0.f, omb2 = 0.f, eps = 0.f;
 };
 
+// Adam of this group's layer-1 weights runs inside the kernel that produces their gradient (which then never
+// reaches HBM): staged backward path, identity features, and the caller did not ask for the gradients
+bool adam_fused(const dgn_graph *g, const Group &G, const AdamStep &adam) {
+    return adam.alpha != 0.f && G.tstaged && !G.gen_feat && g->fuse_adam && !g->keep_grads;
+}
+
 void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam) {
     const int P1 = g->P1;
     const bool drop = rate > 0.f;
@@ -1046,6 +1054,7 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam) {
         }
         PhaseScope ph(g, "spmm_bwd1", gi, G.lane);
         if (G.gen_feat) {  // G1_k = A_k^T dS1, then dW1_k = (X_j (.) m_k / q)^T G1_k
+            G.w1_grad_stale = false;
             spmm_bwd(G, P1, G.G1buf, (long long)G.Kl * G.n_j, nullptr, false);
             NodeType &Tj = g->types[G.j];
             FeatArgs f = {};
@@ -1056,7 +1065,8 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam) {
             g->launches++;
             continue;
         }
-        spmm_bwd(G, P1, g->grads + G.w1_off, (long long)G.Kl * G.F_j, drop ? G.mask1 : nullptr, adam.alpha != 0.f && G.tstaged && g->fuse_adam);
+        G.w1_grad_stale = adam_fused(g, G, adam);
+        spmm_bwd(G, P1, g->grads + G.w1_off, (long long)G.Kl * G.F_j, drop ? G.mask1 : nullptr, G.w1_grad_stale);
     }
     for (auto &d : deferred_dw2) run_dw2(d.first, d.second);
     join_lanes(g, false);
@@ -1632,7 +1642,19 @@ extern "C" int dgn_params_get(dgn_graph *g, int kind, int group, int k, float *v
 extern "C" int dgn_grads_get(dgn_graph *g, int kind, int group, int k, float *values_out, int64_t n) {
     DGN_API_BEGIN
     DGN_REQUIRE(g, "null graph");
+    if (kind == DGN_PARAM_W1 && group >= 0 && group < g->n_groups && g->groups[group].w1_grad_stale)
+        DGN_FAIL(DGN_ERR_INVALID,
+                 "group %d: the last step fused the Adam update of the layer-1 weights into the kernel that produces their "
+                 "gradient, which was never stored; call dgn_keep_gradients(g, 1) before the step (or run it with apply_update = 0)",
+                 group);
     param_io(g, g->grads, kind, group, k, values_out, n, false);
+    DGN_API_END
+}
+
+extern "C" int dgn_keep_gradients(dgn_graph *g, int keep) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(g, "null graph");
+    g->keep_grads = keep != 0;
     DGN_API_END
 }
 
@@ -1818,7 +1840,7 @@ extern "C" int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t
             }
         };
         for (auto &Gq : g->groups)
-            if (Gq.tstaged && !Gq.gen_feat && g->fuse_adam && adam.alpha != 0.f) {
+            if (adam_fused(g, Gq, adam)) {
                 flush(Gq.w1_off);
                 begin = Gq.w1_off + (size_t)Gq.Kl * Gq.F_j * g->d1;
             }

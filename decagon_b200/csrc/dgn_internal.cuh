@@ -232,6 +232,17 @@ struct PredictArgs {
     float *out;               // [count][n_i][n_j]
 };
 
+// TF-1.8 ApplyAdam on one element (optimizer.py:111-113; training_ops.cc ApplyAdam: m += (g - m)(1 - b1);
+// v += (g g - v)(1 - b2); p -= m alpha / (sqrt(v) + eps)).  Explicit round-to-nearest intrinsics, no FMA
+// contraction: the separate adam_kernel and the update fused into spmm_tstaged_kernel round identically (and like
+// the float32 numpy restatement in oracle/decagon_oracle.py AdamTF1).
+__device__ __forceinline__ void adam_update(float &p, float &m, float &v, float g, float alpha, float omb1, float omb2,
+                                            float eps) {
+    m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), omb1));
+    v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), omb2));
+    p = __fsub_rn(p, __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), eps)));
+}
+
 // ---------------------------------------------------------------- kernel launchers (host)
 void launch_spmm(const SpmmArgs &a, int P, cudaStream_t s);
 void launch_seg_reduce(const SpmmArgs &a, const int *multi_rows, int n_multi, int P, cudaStream_t s);

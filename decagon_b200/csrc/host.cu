@@ -89,6 +89,9 @@ extern "C" int dgn_csr_from_coo(int32_t n_rows, int32_t n_cols, int64_t nnz, con
         return DGN_OK;
     } catch (const Failure &f) {
         return f.code;
+    } catch (const std::exception &e) {  // std::bad_alloc and friends must not cross the C ABI
+        set_error("host error: %s", e.what());
+        return DGN_ERR_INVALID;
     }
 }
 
@@ -113,5 +116,8 @@ extern "C" int dgn_sampler_thresholds(const double *degrees, int32_t n, uint32_t
         return DGN_OK;
     } catch (const Failure &f) {
         return f.code;
+    } catch (const std::exception &e) {  // std::bad_alloc and friends must not cross the C ABI
+        set_error("host error: %s", e.what());
+        return DGN_ERR_INVALID;
     }
 }

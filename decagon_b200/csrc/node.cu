@@ -261,9 +261,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float *__restrict__ p, const 
         float *pp = &P4.x, *gg = &G4.x, *mm = &M4.x, *vv = &V4.x;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            mm[q] += (gg[q] - mm[q]) * omb1;
-            vv[q] += (gg[q] * gg[q] - vv[q]) * omb2;
-            pp[q] -= (mm[q] * alpha) / (sqrtf(vv[q]) + eps);
+            adam_update(pp[q], mm[q], vv[q], gg[q], alpha, omb1, omb2, eps);
         }
         reinterpret_cast<float4 *>(p)[i] = P4;
         reinterpret_cast<float4 *>(m)[i] = M4;
@@ -272,9 +270,9 @@ __global__ void __launch_bounds__(256) adam_kernel(float *__restrict__ p, const 
     for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
         float mi = m[i], vi = v[i];
         const float gi = g[i];
-        mi += (gi - mi) * omb1;
-        vi += (gi * gi - vi) * omb2;
-        p[i] -= (mi * alpha) / (sqrtf(vi) + eps);
+        float pi = p[i];
+        adam_update(pi, mi, vi, gi, alpha, omb1, omb2, eps);
+        p[i] = pi;
         m[i] = mi;
         v[i] = vi;
     }

@@ -574,9 +574,7 @@ __global__ void __launch_bounds__(kStagedThreads, 1) spmm_tstaged_kernel(const T
                         float *pq = &P4.x, *mq = &M4.x, *vq = &V4.x;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            mq[q] += (gg[q] - mq[q]) * a.omb1;
-                            vq[q] += (gg[q] * gg[q] - vq[q]) * a.omb2;
-                            pq[q] -= (mq[q] * a.alpha) / (sqrtf(vq[q]) + a.eps);
+                            adam_update(pq[q], mq[q], vq[q], gg[q], a.alpha, a.omb1, a.omb2, a.eps);
                         }
                         *reinterpret_cast<float4 *>(a.adam_p + o) = P4;
                         *reinterpret_cast<float4 *>(a.adam_m + o) = M4;

@@ -75,6 +75,21 @@ def _contains(pair, edges):
     return bool(np.any((edges[:, 0] == pair[0]) & (edges[:, 1] == pair[1])))
 
 
+class FeedDict(dict):
+    """A plain feed dict plus ``graph_token``: set by ``update_feed_dict`` when every adjacency / feature entry
+    is the iterator's own tuple, cleared as soon as the caller replaces one of them."""
+    graph_token = None
+
+    def __setitem__(self, key, value):
+        if getattr(key, 'sparse', False):
+            self.graph_token = None
+        dict.__setitem__(self, key, value)
+
+    def update(self, *args, **kwargs):
+        self.graph_token = None
+        dict.update(self, *args, **kwargs)
+
+
 class EdgeMinibatchIterator(object):
     """Iterates over batches of training edges of one relation at a time.
 
@@ -223,25 +238,39 @@ class EdgeMinibatchIterator(object):
     def end(self):
         return len(self.freebatch_edge_types) == 0
 
+    def _graph_feed(self, placeholders):
+        """{placeholder: tuple} of every adjacency and feature tuple, built once per placeholder dict."""
+        cached = getattr(self, '_graph_feed_cache', None)
+        if cached is None or cached[0] is not placeholders:
+            entries = {}
+            for i, j in self.edge_types:
+                for k in range(self.edge_types[i, j]):
+                    entries[placeholders['adj_mats_%d,%d,%d' % (i, j, k)]] = self.adj_train[i, j][k]
+            for i, _ in self.edge_types:
+                entries[placeholders['feat_%d' % i]] = self.feat[i]
+            self._graph_feed_cache = cached = (placeholders, entries)
+        return cached[1]
+
     def update_feed_dict(self, feed_dict, dropout, placeholders):
         """Adds every adjacency tuple, the feature tuples and the dropout rate
         (``minibatch.py:259-267``).  The tuples are the SAME objects on every call, which is
-        what lets ``decagon_b200.session.Session`` keep them resident on the device."""
-        for i, j in self.edge_types:
-            for k in range(self.edge_types[i, j]):
-                feed_dict[placeholders['adj_mats_%d,%d,%d' % (i, j, k)]] = self.adj_train[i, j][k]
-        for i, _ in self.edge_types:
-            feed_dict[placeholders['feat_%d' % i]] = self.feat[i]
-        feed_dict[placeholders['dropout']] = dropout
+        what lets ``decagon_b200.session.Session`` keep them resident on the device; a ``FeedDict``
+        (what ``batch_feed_dict`` returns) also carries a token naming this iterator's graph, so the
+        session does not have to compare the 1932 tuples of the polypharmacy shape on every run."""
+        dict.update(feed_dict, self._graph_feed(placeholders))
+        dict.__setitem__(feed_dict, placeholders['dropout'], dropout)
+        if isinstance(feed_dict, FeedDict):
+            feed_dict.graph_token = (id(self), id(placeholders))
+            feed_dict._graph_owner = self  # keeps id(self) unique while the feed dict lives
         return feed_dict
 
     def batch_feed_dict(self, batch_edges, batch_edge_type, placeholders):
-        return {
+        return FeedDict({
             placeholders['batch']: batch_edges,
             placeholders['batch_edge_type_idx']: batch_edge_type,
             placeholders['batch_row_edge_type']: self.idx2edge_type[batch_edge_type][0],
             placeholders['batch_col_edge_type']: self.idx2edge_type[batch_edge_type][1],
-        }
+        })
 
     def next_minibatch_feed_dict(self, placeholders):
         """Round-robin schedule of ``minibatch.py:278-313``: the fixed relations

@@ -198,6 +198,11 @@ class Engine(object):
     def get_grads(self):
         return self._collect(self.get_grad)
 
+    def keep_gradients(self, keep=True):
+        """Materialise every gradient also in steps that apply the update (no fused Adam): needed to fetch
+        ``opt.grads_vars`` together with ``opt.opt_op`` (optimizer.py:111-114)."""
+        check(self.lib.dgn_keep_gradients(self._h, 1 if keep else 0))
+
     def n_params(self):
         n = ctypes.c_int64(0)
         check(self.lib.dgn_params_count(self._h, ctypes.byref(n)))

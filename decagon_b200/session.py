@@ -35,6 +35,9 @@ class Session(object):
     # ------------------------------------------------------------------ engine lifetime
     def _engine(self, model, feed):
         eng = model.engine
+        token = getattr(feed, 'graph_token', None)
+        if eng is not None and token is not None and token == eng._graph_token and eng.finalized and eng._degrees_set:
+            return eng  # the iterator vouches for its tuples (minibatch.FeedDict): nothing to compare
         adj_ph = model.adj_mats
         groups = model.groups()
         if eng is None:
@@ -44,7 +47,17 @@ class Session(object):
                 n_nodes[g[0]], n_nodes[g[1]] = int(tup[2][0]), int(tup[2][1])
             eng = Engine(n_nodes, model.input_dim, model.edge_types, model.decoders, model.hidden1_dim,
                          model.hidden2_dim, device=self.device)
-            eng._fed_ids, eng._initialized = {}, False
+            eng._fed_ids, eng._initialized, eng._graph_token, eng._degrees_set, eng._keep = {}, False, None, False, {}
+            self._dist = None
+            world = int(os.environ.get('WORLD_SIZE', '1'))
+            if world > 1:
+                # one process per GPU (torchrun): the many-relation groups are partitioned over the ranks;
+                # torch.distributed is only the control plane that carries the exchange handles
+                import torch.distributed as dist
+                if not dist.is_initialized():
+                    raise RuntimeError('WORLD_SIZE > 1: call torch.distributed.init_process_group first')
+                eng.comm_init(dist.get_rank(), dist.get_world_size())
+                self._dist = dist
             model.engine = eng
         dirty = False
         for r, (g, k) in enumerate(eng.flat):
@@ -52,23 +65,24 @@ class Session(object):
             if ph in feed and eng._fed_ids.get(ph) != id(feed[ph]):
                 eng.set_relation(r, *feed[ph])
                 eng._fed_ids[ph] = id(feed[ph])
-                eng._keep = getattr(eng, '_keep', {})
                 eng._keep[ph] = feed[ph]  # keep the tuple alive so its id stays unique
                 dirty = True
         for t, ph in model.inputs.items():
             if ph in feed and eng._fed_ids.get(ph) != id(feed[ph]):
                 eng.set_features(t, *feed[ph])
                 eng._fed_ids[ph] = id(feed[ph])
-                eng._keep = getattr(eng, '_keep', {})
                 eng._keep[ph] = feed[ph]
                 dirty = True
         opt = getattr(model, 'optimizer', None)
-        if opt is not None and not getattr(eng, '_degrees_set', False):
+        if opt is not None and not eng._degrees_set:
             for r, (g, k) in enumerate(eng.flat):
                 eng.set_degrees(r, opt.degrees[g[0]][k])
             eng._degrees_set = True
         if dirty or not eng.finalized:
             eng.finalize()
+            if getattr(self, '_dist', None) is not None:
+                eng.connect(self._dist)
+        eng._graph_token = token
         return eng
 
     @staticmethod
@@ -136,9 +150,7 @@ class Session(object):
         opt = getattr(model, 'optimizer', None)
         dropout = float(np.float32(self._fed(feed, model.dropout)))
         step_kinds = {'opt_op', 'cost', 'outputs', 'neg_outputs', 'neg_samples', 'grad'}
-        if kinds & {'preds', 'neg_preds'}:
-            raise NotImplementedError('the B x B score matrices preds / neg_preds are never materialised; '
-                                      'fetch outputs / neg_outputs (their diagonals, optimizer.py:52,56)')
+        step_kinds |= {'preds', 'neg_preds'}
         loss = None
         if kinds & step_kinds:
             batch = np.asarray(self._fed(feed, opt.inputs))
@@ -149,6 +161,7 @@ class Session(object):
             g, _ = eng.flat[r]
             if (int(self._fed(feed, opt.batch_row_edge_type)), int(self._fed(feed, opt.batch_col_edge_type))) != g:
                 raise ValueError('batch_row_edge_type / batch_col_edge_type do not match relation %d = %s' % (r, g))
+            eng.keep_gradients('grad' in kinds)  # [opt_op, grads_vars]: no fused Adam, every gradient is stored
             loss = eng.train_step(r, batch, negatives=None, loss=opt.loss_kind, margin=opt.margin,
                                   neg_weight=opt.neg_sample_weights, lr=opt.learning_rate, dropout=dropout,
                                   seed=self.seed, step=self.step, apply_update='opt_op' in kinds)
@@ -172,6 +185,16 @@ class Session(object):
                 if batch_out is None:
                     batch_out = eng.last_batch_outputs(opt.batch_size)
                 results[idx] = batch_out[{'outputs': 0, 'neg_outputs': 1, 'neg_samples': 2}[kind]]
+            elif kind in ('preds', 'neg_preds'):
+                # batch_predict (optimizer.py:51,55,63-85): the full B x B matrix of the step's embeddings -- only
+                # its diagonal enters the loss; scored on the device pair by pair, never on the training path
+                if batch_out is None:
+                    batch_out = eng.last_batch_outputs(opt.batch_size)
+                batch = np.asarray(self._fed(feed, opt.inputs))
+                rows = batch[:, 0] if kind == 'preds' else batch_out[2]
+                pairs = np.stack([np.repeat(rows, opt.batch_size), np.tile(batch[:, 1], opt.batch_size)], axis=1)
+                r = int(self._fed(feed, opt.batch_edge_type_idx))
+                results[idx] = eng.predict_edges(r, pairs, sigmoid=False).reshape(opt.batch_size, opt.batch_size)
             elif kind in ('row_inputs', 'col_inputs'):
                 batch = np.asarray(self._fed(feed, opt.inputs))
                 results[idx] = batch[:, 0 if kind == 'row_inputs' else 1].astype(np.int32)

@@ -164,6 +164,11 @@ int dgn_last_batch_outputs(dgn_graph *g, float *pos_out, float *neg_out, int64_t
  * with apply_update == 0 materialises every gradient: with apply_update != 0 the Adam update of the
  * layer-1 weights of the many-relation groups is fused into the kernel that produces their gradient. */
 int dgn_grads_get(dgn_graph *g, int kind, int group, int k, float *values_out, int64_t n);
+/* keep != 0: every later dgn_train_step materialises every gradient even with apply_update != 0 (the fused
+ * update is replaced by the separate Adam kernel; same parameters bit for bit) -- what fetching
+ * [opt.opt_op, opt.grads_vars] in one session.run needs (optimizer.py:111-114).  Without it dgn_grads_get
+ * fails for the layer-1 weights whose gradient the fused step never stored. */
+int dgn_keep_gradients(dgn_graph *g, int keep);
 
 /* optimizer.predictions (optimizer.py:87-106): Z_i loc glb loc Z_j^T of relation r from the
  * CURRENT embeddings (call dgn_encoder_forward first), row-major [n_i, n_j]. */

@@ -24,6 +24,19 @@ def mini_poly(n_types=12, seed=0, features=None):
                                        features=features)
 
 
+def rel_l2(a, b):
+    """||a - b||_2 / ||b||_2 over the whole tensor."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-30)) if b.size else 0.0
+
+
+def assert_close(a, b, tol, what=None):
+    """Both metrics of the parity contract: max|a-b| / max|b| and ||a-b||_2 / ||b||_2, each <= tol."""
+    e_max, e_l2 = rel_err(a, b), rel_l2(a, b)
+    assert e_max <= tol and e_l2 <= tol, (what, 'max-norm rel-err %.3e' % e_max, 'l2 rel-err %.3e' % e_l2)
+    return max(e_max, e_l2)
+
+
 class Case(object):
     def __init__(self, inputs, iterator_seed=0, param_seed=1, batch_size=512, val_test_size=0.05, hidden1=64):
         self.inputs = inputs

@@ -351,3 +351,80 @@ def test_greedy_candidate_ranking_on_device():
     assert len(ranker.possibilities) == len(poss) - 100 and sum(m.sum() for m in masks.values()) <= 100
     assert num_to_unmask(1000, 0) == 10 and num_to_unmask(1000, 3) == 40 and num_to_unmask(1000, 7) == 360
     eng.close()
+
+
+def test_preds_matrices_and_grads_fetched_with_opt_op():
+    """optimizer.preds / neg_preds (the B x B matrices of optimizer.py:51,55 whose diagonals are outputs /
+    neg_outputs) and [opt_op, grads_vars] in ONE run (optimizer.py:111-114) on a graph that takes the staged path,
+    where the Adam update of the layer-1 weights is normally fused into the gradient kernel: the fetched gradients
+    must be the real ones (float64 oracle, 1e-5) and the update must still be applied."""
+    inputs = common.mini_poly(n_types=10, seed=5)
+    B = 64
+    placeholders, minibatch, model, opt = build_trainable(inputs, batch_size=B)
+    sess = tf.Session(seed=SEED)
+    sess.run(tf.global_variables_initializer())
+    graph = O.Graph.from_iterator(minibatch, inputs.edge_type2decoder)
+    p = O.cast_params(oracle_params(model), np.float64)
+    np.random.seed(1)
+    minibatch.shuffle()
+    fd = minibatch.update_feed_dict(minibatch.next_minibatch_feed_dict(placeholders), 0.1, placeholders)
+    while fd[placeholders['batch_row_edge_type']] != 1 or fd[placeholders['batch_col_edge_type']] != 1:
+        fd = minibatch.update_feed_dict(minibatch.next_minibatch_feed_dict(placeholders), 0.1, placeholders)
+    grad_fetches = [gv[0] for gv in opt.grads_vars]
+    outs = sess.run([opt.opt_op, opt.cost, opt.preds, opt.neg_preds, opt.outputs, opt.neg_outputs, opt.neg_samples]
+                    + grad_fetches, feed_dict=fd)
+    preds, neg_preds, pos, neg, negs = outs[2:7]
+    assert preds.shape == neg_preds.shape == (B, B)
+    assert rel_err(np.diag(preds), pos) <= 1e-6 and rel_err(np.diag(neg_preds), neg) <= 1e-6
+    r = int(fd[placeholders['batch_edge_type_idx']])
+    g, k = graph.flat[r]
+    batch = fd[placeholders['batch']]
+    masks = O.masks_for(graph, 0.1, 0, SEED)
+    loss, opos, oneg, grads, Z = O.train_step_grads(graph, p, g, k, batch, negs, 0.1, masks, 'hinge')
+    glb, loc = O.relation_matrices(graph, p, g, k)
+    want = (((Z[g[0]][batch[:, 0]] @ loc) @ glb) @ loc) @ Z[g[1]][batch[:, 1]].T
+    assert rel_err(preds, want) <= 1e-5
+    assert abs(float(outs[1]) - loss) <= 1e-5 * max(1.0, abs(loss))
+    names = {_lib_kind: n for n, _lib_kind in (('W1', 0), ('W2', 1), ('R', 2), ('D', 3))}
+    checked = 0
+    for (_, var), got in zip(opt.grads_vars, outs[7:]):
+        kind, gg, kk = var.slot
+        ref = grads[names[kind]][gg] if kind == 2 else grads[names[kind]][gg][kk]
+        if np.abs(ref).max() > 0:
+            assert rel_err(got, ref) <= 1e-5, (var.name, rel_err(got, ref))
+            checked += 1
+        else:
+            assert np.abs(got).max() <= 1e-12, var.name
+    assert checked > 20
+    # the update was applied all the same: the staged group's layer-1 weights moved
+    w = sess.run(model.layer1[1, 1].vars['weights_0'])
+    assert np.abs(w - model.layer1[1, 1].vars['weights_0'].initial).max() > 1e-4
+
+
+def test_feed_dict_token_skips_the_tuple_walk():
+    """update_feed_dict on the iterator's FeedDict carries a token: later runs neither compare nor upload the
+    adjacency tuples; replacing one tuple by hand drops the token and the new tuple is uploaded."""
+    inputs = datasets.toy_graph()
+    placeholders, minibatch, model, opt = build_trainable(inputs)
+    sess = tf.Session(seed=3)
+    sess.run(tf.global_variables_initializer())
+    fd = minibatch.update_feed_dict(minibatch.next_minibatch_feed_dict(placeholders), 0.1, placeholders)
+    assert fd.graph_token is not None
+    sess.run([opt.opt_op, opt.cost], feed_dict=fd)
+    eng = model.engine
+    assert eng._graph_token == fd.graph_token
+    walked = []
+    eng._fed_ids = type('Spy', (dict,), {'get': lambda self, k, d=None: (walked.append(k), dict.get(self, k, d))[1]})(eng._fed_ids)
+    fd = minibatch.update_feed_dict(minibatch.next_minibatch_feed_dict(placeholders), 0.1, placeholders)
+    sess.run([opt.opt_op, opt.cost], feed_dict=fd)
+    assert walked == []
+    fd[placeholders['dropout']] = 0.0       # an ordinary key keeps the token
+    assert fd.graph_token is not None
+    key = placeholders['adj_mats_1,1,0']
+    c, v, s_ = fd[key]
+    fd[key] = (c.copy(), v.copy(), s_)      # a sparse placeholder drops it
+    assert fd.graph_token is None
+    sess.run([opt.opt_op, opt.cost], feed_dict=fd)
+    assert len(walked) >= sum(inputs.edge_types.values())
+    plain = dict(minibatch.update_feed_dict(minibatch.next_minibatch_feed_dict(placeholders), 0.1, placeholders))
+    sess.run([opt.opt_op, opt.cost], feed_dict=plain)   # plain dicts keep working (slow path)
