@@ -9,6 +9,7 @@
 #include <memory>
 #include <numeric>
 #include <queue>
+#include <tuple>
 
 #include "dgn_internal.cuh"
 #include "philox.cuh"
@@ -391,6 +392,9 @@ struct dgn_graph {
     uint32_t **peer_flags_dev = nullptr;
     bool connected = false;
     int n_exchanges = 0;
+    unsigned long long exchange_timeout_ns = 600ull * 1000000000ull;  // DGN_EXCHANGE_TIMEOUT_S, wall clock
+    int *exchange_error = nullptr;   // device: 1 + rank of the peer whose stamp never arrived
+    int *exchange_error_host = nullptr;
     bool two_lanes = true;
     bool fuse_adam = true;  // Adam of the layer-1 weights inside the kernel that produces their gradient
     bool keep_grads = false;  // dgn_keep_gradients: every gradient is materialised (no fused Adam)
@@ -400,14 +404,26 @@ struct dgn_graph {
     size_t n_params = 0, dec_off = 0;
     float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
     float beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f, b1p = 0.9f, b2p = 0.999f;
-    // minibatch staging
+    // per-step block [StepDyn | negatives | batch]: pinned host ring + ONE device mirror, one H2D copy per step
     static const int kRing = 4;
-    int *batch_host[kRing] = {nullptr, nullptr, nullptr, nullptr};
-    long long *neg_host[kRing] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned char *step_host[kRing] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned char *step_dev = nullptr;
+    size_t step_neg_off = 0, step_batch_off = 0;
     cudaEvent_t ring_ev[kRing];
     int ring_cap = 0, ring_pos = 0;
+    StepDyn *dyn_dev = nullptr;
     int *batch_dev = nullptr;
     long long *neg_dev = nullptr, *neg_out = nullptr;
+    // CUDA graphs of the training step, one per (dropout rate, update / gradients mode, exchange parities)
+    struct StepGraph {
+        int seen = 0;
+        cudaGraphExec_t exec = nullptr;
+        long long launches = 0;
+    };
+    std::map<std::tuple<uint32_t, int, int, int>, StepGraph> step_graphs;
+    bool use_graphs = true;   // DGN_CUDA_GRAPH=0: issue every kernel from the host each step
+    bool capturing = false;
+    long long graph_replays = 0;
     float *pos_out = nullptr, *negs_out = nullptr, *loss_dev = nullptr, *loss_host = nullptr;
     float *decode_scratch = nullptr;
     unsigned *decode_ticket = nullptr;
@@ -476,6 +492,18 @@ void join_lanes(dgn_graph *g, bool both) {
 
 size_t panel_floats(int P, long long rows) { return (size_t)P * (size_t)rows * 32; }
 
+// after a stream synchronisation: did an exchange give up on a peer?
+void check_exchange(dgn_graph *g) {
+    if (g->world == 1 || !g->exchange_error) return;
+    CUDA_CHECK(cudaMemcpy(g->exchange_error_host, g->exchange_error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (*g->exchange_error_host != 0) {
+        const int peer = *g->exchange_error_host - 1;
+        CUDA_CHECK(cudaMemset(g->exchange_error, 0, sizeof(int)));
+        DGN_FAIL(DGN_ERR_CUDA, "multi-GPU exchange timed out waiting for rank %d (every rank must call dgn_encoder_forward / "
+                 "dgn_train_step in lock step; DGN_EXCHANGE_TIMEOUT_S sets the limit)", peer);
+    }
+}
+
 void check_finalized(dgn_graph *g) { DGN_REQUIRE(g && g->finalized, "graph is not finalized (call dgn_graph_finalize)"); }
 
 void free_group_device(Group &G) {
@@ -513,7 +541,7 @@ void build_group(dgn_graph *g, Group &G) {
     }
     const std::vector<HostCsr> &rel = G.partitioned ? local_copy : G.rel;
     {
-        std::vector<int> ids((size_t)K + 1, 0);  // + 1: the packed layer-1 mask rounds its bit count up to a word
+        std::vector<int> ids((size_t)K + 33, 0);  // + 33: the last word of the packed layer-1 mask may walk past up to 32 relation ends
         for (int l = 0; l < K; ++l) ids[l] = G.r0 + G.loc[l];
         G.rel_ids = dev_upload(ids);
     }
@@ -695,11 +723,11 @@ void build_comm(dgn_graph *g) {
 // same order.
 void exchange(dgn_graph *g, Group &G, int x, const float *partial, int n_chunks, cudaStream_t s) {
     DGN_REQUIRE(g->connected, "dgn_comm_connect was not called");
-    Group::Exchange &X = G.xch[x];
-    ++X.stamp;
+    Group::Exchange &X = G.xch[x];  // X.stamp: this step's stamp (begin_step)
     float *mine = reinterpret_cast<float *>(g->comm + X.off) + (X.stamp & 1) * X.floats;
     launch_publish(partial, n_chunks, X.floats, mine, s);
-    launch_signal_wait(g->peer_flags_dev, reinterpret_cast<uint32_t *>(g->comm), g->rank, g->world, X.id, X.stamp, s);
+    launch_signal_wait(g->peer_flags_dev, reinterpret_cast<uint32_t *>(g->comm), g->rank, g->world, X.id, g->dyn_dev, g->exchange_timeout_ns,
+                       g->exchange_error, s);
     g->launches += 2;
 }
 const float *peer_ptr(dgn_graph *g, const Group &G, int x, int r) {
@@ -729,7 +757,7 @@ struct StepDeps {
     std::vector<Dep> H, Z, dZ, dA; // per node type
 };
 
-void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step, StepDeps &D) {
+void run_forward(dgn_graph *g, float rate, StepDeps &D) {
     const int P1 = g->P1;
     const bool drop = rate > 0.f;
     const float keep = 1.f - rate;
@@ -737,17 +765,20 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step, StepDep
     D.S1.assign(g->n_groups, Dep()), D.S2.assign(g->n_groups, Dep()), D.dH.assign(g->n_groups, Dep());
     D.H.assign(g->n_types, Dep()), D.Z.assign(g->n_types, Dep()), D.dZ.assign(g->n_types, Dep()), D.dA.assign(g->n_types, Dep());
     g->dep_next = 0;
-    join_lanes(g, true);  // lane 1 starts after everything queued so far (previous step's Adam, parameter uploads)
+    if (g->two_lanes) {  // lane 1 starts after everything queued so far (previous step's Adam, the per-step block)
+        Dep d;           // (every call ends with lane 1 joined into lane 0, so nothing is pending there)
+        produced(g, d, 0);
+        consume(g, d, 1);
+    }
     if (drop) {
-        const uint32_t thr = dropout_threshold(rate);
         if (g->two_lanes) {
             CUDA_CHECK(cudaEventRecord(g->mask_go, g->stream));  // after the join: last step's readers of mask2 are done
             CUDA_CHECK(cudaStreamWaitEvent(g->stream3, g->mask_go, 0));
             for (int lane = 1; lane >= 0; --lane)  // small ones first
                 for (auto &G : g->groups) {
                     if (G.lane != lane) continue;
-                    launch_gen_mask(G.mask2, G.mask2_words, (long long)G.n_j * g->d1, G.n_j * P1, G.rel_ids, kStreamDropout2, step, seed,
-                                    thr, g->stream3);
+                    launch_gen_mask(G.mask2, G.mask2_words, (long long)G.n_j * g->d1, G.n_j * P1, G.rel_ids, kStreamDropout2, g->dyn_dev,
+                                    g->stream3);
                     g->launches++;
                 }
             CUDA_CHECK(cudaEventRecord(g->mask_done, g->stream3));
@@ -758,7 +789,7 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step, StepDep
             PhaseScope ph(g, "mask", -1, 0);
             MaskBatch mb = {};
             auto flush = [&]() {
-                launch_gen_mask_multi(mb, kStreamDropout1, step, seed, thr, g->stream);
+                launch_gen_mask_multi(mb, kStreamDropout1, g->dyn_dev, g->stream);
                 if (mb.n) g->launches++;
                 mb.n = 0;
             };
@@ -774,7 +805,7 @@ void run_forward(dgn_graph *g, float rate, uint64_t seed, uint32_t step, StepDep
             consume(g, d, 1);
         } else {
             for (auto &G : g->groups) {
-                launch_gen_mask(G.mask2, G.mask2_words, (long long)G.n_j * g->d1, G.n_j * P1, G.rel_ids, kStreamDropout2, step, seed, thr,
+                launch_gen_mask(G.mask2, G.mask2_words, (long long)G.n_j * g->d1, G.n_j * P1, G.rel_ids, kStreamDropout2, g->dyn_dev,
                                 g->stream);
                 g->launches++;
             }
@@ -944,7 +975,7 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam) {
             if (fuse_adam) {
                 const size_t off = (size_t)(out - g->grads);
                 a.adam_p = g->params + off, a.adam_m = g->adam_m + off, a.adam_v = g->adam_v + off;
-                a.alpha = adam.alpha, a.omb1 = adam.omb1, a.omb2 = adam.omb2, a.eps = adam.eps;
+                a.dyn = g->dyn_dev;
             }
             launch_spmm_tstaged(a, s);
             g->launches++;
@@ -1054,7 +1085,6 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam) {
         }
         PhaseScope ph(g, "spmm_bwd1", gi, G.lane);
         if (G.gen_feat) {  // G1_k = A_k^T dS1, then dW1_k = (X_j (.) m_k / q)^T G1_k
-            G.w1_grad_stale = false;
             spmm_bwd(G, P1, G.G1buf, (long long)G.Kl * G.n_j, nullptr, false);
             NodeType &Tj = g->types[G.j];
             FeatArgs f = {};
@@ -1065,8 +1095,7 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam) {
             g->launches++;
             continue;
         }
-        G.w1_grad_stale = adam_fused(g, G, adam);
-        spmm_bwd(G, P1, g->grads + G.w1_off, (long long)G.Kl * G.F_j, drop ? G.mask1 : nullptr, G.w1_grad_stale);
+        spmm_bwd(G, P1, g->grads + G.w1_off, (long long)G.Kl * G.F_j, drop ? G.mask1 : nullptr, adam_fused(g, G, adam));
     }
     for (auto &d : deferred_dw2) run_dw2(d.first, d.second);
     join_lanes(g, false);
@@ -1163,26 +1192,60 @@ void arena_read(dgn_graph *g, const float *arena, const ParamSpan &s, float *val
     unpack_panels(tmp.data(), values, s.rows, g->P1);
 }
 
+void drop_step_graphs(dgn_graph *g) {
+    for (auto &kv : g->step_graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    g->step_graphs.clear();
+}
+
 void ensure_batch_capacity(dgn_graph *g, int B) {
     if (B <= g->ring_cap) return;
     CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    drop_step_graphs(g);  // they hold the old addresses
+    const int cap = std::max(B, 1024);
+    g->step_neg_off = (sizeof(StepDyn) + 15) / 16 * 16;
+    g->step_batch_off = g->step_neg_off + (size_t)cap * sizeof(long long);
+    const size_t total = g->step_batch_off + (size_t)cap * 2 * sizeof(int);
     for (int i = 0; i < dgn_graph::kRing; ++i) {
-        if (g->batch_host[i]) cudaFreeHost(g->batch_host[i]);
-        if (g->neg_host[i]) cudaFreeHost(g->neg_host[i]);
-        CUDA_CHECK(cudaMallocHost(&g->batch_host[i], (size_t)B * 2 * sizeof(int)));
-        CUDA_CHECK(cudaMallocHost(&g->neg_host[i], (size_t)B * sizeof(long long)));
+        if (g->step_host[i]) cudaFreeHost(g->step_host[i]);
+        CUDA_CHECK(cudaMallocHost(&g->step_host[i], total));
+        memset(g->step_host[i], 0, total);
     }
-    dev_free(g->batch_dev);
-    dev_free(g->neg_dev);
+    dev_free(g->step_dev);
     dev_free(g->neg_out);
     dev_free(g->pos_out);
     dev_free(g->negs_out);
-    g->batch_dev = dev_alloc<int>((size_t)B * 2);
-    g->neg_dev = dev_alloc<long long>(B);
-    g->neg_out = dev_alloc<long long>(B);
-    g->pos_out = dev_alloc<float>(B);
-    g->negs_out = dev_alloc<float>(B);
-    g->ring_cap = B;
+    g->step_dev = dev_alloc<unsigned char>(total);
+    CUDA_CHECK(cudaMemset(g->step_dev, 0, total));
+    g->dyn_dev = reinterpret_cast<StepDyn *>(g->step_dev);
+    g->neg_dev = reinterpret_cast<long long *>(g->step_dev + g->step_neg_off);
+    g->batch_dev = reinterpret_cast<int *>(g->step_dev + g->step_batch_off);
+    g->neg_out = dev_alloc<long long>(cap);
+    g->pos_out = dev_alloc<float>(cap);
+    g->negs_out = dev_alloc<float>(cap);
+    g->ring_cap = cap;
+}
+
+// Next pinned slot of the ring with the per-step header filled in: dropout stream words, Adam coefficients (when
+// given) and the stamps of the exchanges this call will run (n_exchanges_per_group: 2 = forward only, 3 = a whole
+// training step).  The caller adds the decode arguments / batch and calls commit_step.
+int begin_step(dgn_graph *g, float rate, uint64_t seed, uint32_t step, int n_exchanges_per_group) {
+    ensure_batch_capacity(g, 1);
+    const int slot = g->ring_pos;
+    g->ring_pos = (g->ring_pos + 1) % dgn_graph::kRing;
+    CUDA_CHECK(cudaEventSynchronize(g->ring_ev[slot]));
+    StepDyn *h = reinterpret_cast<StepDyn *>(g->step_host[slot]);
+    memset(h, 0, sizeof(StepDyn));
+    h->step = step, h->seed_lo = (uint32_t)(seed & 0xffffffffu), h->seed_hi = (uint32_t)(seed >> 32);
+    h->threshold = dropout_threshold(rate);
+    for (auto &G : g->groups)
+        if (G.partitioned)
+            for (int x = 0; x < n_exchanges_per_group; ++x) h->stamp[G.xch[x].id] = ++G.xch[x].stamp;
+    return slot;
+}
+void commit_step(dgn_graph *g, int slot, size_t bytes) {
+    CUDA_CHECK(cudaMemcpyAsync(g->step_dev, g->step_host[slot], bytes, cudaMemcpyHostToDevice, g->stream));
+    CUDA_CHECK(cudaEventRecord(g->ring_ev[slot], g->stream));
 }
 
 // all-pairs scores: tensor cores (tcgen05, 3 x TF32) unless DGN_PREDICT_FFMA=1 asks for the CUDA-core kernel
@@ -1372,6 +1435,11 @@ extern "C" int dgn_graph_create(dgn_graph **out, int device, int n_types, const 
     g->own_stream = true;
     for (int i = 0; i < dgn_graph::kRing; ++i) CUDA_CHECK(cudaEventCreateWithFlags(&g->ring_ev[i], cudaEventDisableTiming));
     g->loss_dev = dev_alloc<float>(1);
+    g->exchange_error = dev_alloc<int>(1);
+    CUDA_CHECK(cudaMemset(g->exchange_error, 0, sizeof(int)));
+    CUDA_CHECK(cudaMallocHost(&g->exchange_error_host, sizeof(int)));
+    *g->exchange_error_host = 0;
+    if (const char *t = getenv("DGN_EXCHANGE_TIMEOUT_S")) g->exchange_timeout_ns = (unsigned long long)(atof(t) * 1e9);
     g->decode_scratch = dev_alloc<float>((size_t)kDecodeCtas * (32 * 32 + 1));
     g->decode_ticket = dev_alloc<unsigned>(1);
     CUDA_CHECK(cudaMemset(g->decode_ticket, 0, sizeof(unsigned)));
@@ -1393,6 +1461,8 @@ extern "C" int dgn_graph_create(dgn_graph **out, int device, int n_types, const 
     g->fuse_adam = !(env && env[0] == '0');
     env = getenv("DGN_SINGLE_STREAM");
     g->two_lanes = !(env && env[0] == '1');
+    env = getenv("DGN_CUDA_GRAPH");
+    g->use_graphs = !(env && env[0] == '0');
     env = getenv("DGN_DISABLE_TSTAGED");
     g->allow_tstaged = !(env && env[0] == '1');
     *out = g.release();
@@ -1420,18 +1490,19 @@ extern "C" int dgn_graph_destroy(dgn_graph *g) {
     }
     free_arena(g);
     free_comm(g);
-    dev_free(g->batch_dev);
-    dev_free(g->neg_dev);
+    drop_step_graphs(g);
+    dev_free(g->step_dev);
     dev_free(g->neg_out);
     dev_free(g->pos_out);
     dev_free(g->negs_out);
     dev_free(g->loss_dev);
+    dev_free(g->exchange_error);
+    if (g->exchange_error_host) cudaFreeHost(g->exchange_error_host);
     dev_free(g->decode_scratch);
     dev_free(g->decode_ticket);
     if (g->loss_host) cudaFreeHost(g->loss_host);
     for (int i = 0; i < dgn_graph::kRing; ++i) {
-        if (g->batch_host[i]) cudaFreeHost(g->batch_host[i]);
-        if (g->neg_host[i]) cudaFreeHost(g->neg_host[i]);
+        if (g->step_host[i]) cudaFreeHost(g->step_host[i]);
         cudaEventDestroy(g->ring_ev[i]);
     }
     for (auto &p : g->phases) {
@@ -1510,6 +1581,7 @@ extern "C" int dgn_graph_finalize(dgn_graph *g) {
         DGN_REQUIRE(!g->types[G.j].identity || G.F_j == G.n_j, "identity features need feat_dim == n_nodes for type %d", G.j);
     }
     CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    drop_step_graphs(g);  // they hold the addresses of the old device layout
     for (auto &T : g->types) {
         free_csr(T.X);
         free_csr(T.Xt);
@@ -1550,7 +1622,7 @@ extern "C" int dgn_graph_finalize(dgn_graph *g) {
     build_comm(g);
     // no device allocation may happen while a peer waits for this rank inside an exchange: take the batch
     // buffers now (a larger batch later re-allocates; keep the ranks in step around such a change)
-    if (g->world > 1) ensure_batch_capacity(g, 4096);
+    ensure_batch_capacity(g, g->world > 1 ? 4096 : 1024);
     // stream lanes: the groups of many small relations (persistent one-CTA-per-SM kernels) on lane 0, the
     // rest on lane 1 so that their short kernels fill the gaps; per-type kernels follow their row groups
     bool any_staged = false;
@@ -1740,11 +1812,68 @@ extern "C" int dgn_encoder_forward(dgn_graph *g, float dropout, uint64_t seed, u
     check_finalized(g);
     DGN_REQUIRE(dropout >= 0.f && dropout < 1.f, "dropout rate %g outside [0, 1)", dropout);
     CUDA_CHECK(cudaSetDevice(g->device));
+    const int slot = begin_step(g, dropout, seed, step, 2);
+    commit_step(g, slot, sizeof(StepDyn));
     StepDeps deps;
-    run_forward(g, dropout, seed, step, deps);
+    run_forward(g, dropout, deps);
     join_lanes(g, false);
     DGN_API_END
 }
+
+namespace {
+
+// forward + decode + backward + optimizer of one training step, issued on the library's streams (directly, or
+// while lane 0 is being captured into a CUDA graph).  Everything that differs between two steps is read by the
+// kernels from the per-step block in device memory (StepDyn), so the sequence of launches depends only on
+// (dropout on / off and its rate, update or not, gradients kept or not).
+void issue_train_step(dgn_graph *g, float dropout, bool apply_update) {
+    cudaStream_t s = g->stream;
+    StepDeps deps;
+    run_forward(g, dropout, deps);
+    {
+        for (int t = 0; t < g->n_types; ++t) consume(g, deps.Z[t], 0);
+        PhaseScope ph(g, "decode");
+        if (g->n_params > g->dec_off)
+            CUDA_CHECK(cudaMemsetAsync(g->grads + g->dec_off, 0, (g->n_params - g->dec_off) * sizeof(float), s));
+        launch_decode(g->dyn_dev, s);
+        g->launches++;
+        if (g->n_types <= kMaxTypes) {
+            FixedBatch fb = {};
+            for (auto &T : g->types) fb.q[fb.count] = T.dZq, fb.out[fb.count] = T.dZ, fb.n[fb.count] = (size_t)panel_floats(1, T.n), fb.count++;
+            launch_fixed_to_float_clear(fb, s);
+            g->launches++;
+        } else {
+            for (auto &T : g->types) {
+                launch_fixed_to_float(T.dZq, T.dZ, panel_floats(1, T.n), s);
+                g->launches++;
+            }
+        }
+        for (int t = 0; t < g->n_types; ++t) produced(g, deps.dZ[t], 0);
+    }
+    AdamStep adam;
+    adam.alpha = apply_update ? 1.f : 0.f;  // only "is there an update": the coefficients are in the per-step block
+    run_backward(g, dropout, deps, adam);
+    if (apply_update) {
+        PhaseScope ph(g, "adam");
+        // every variable whose update was not fused into the kernel that produced its gradient
+        size_t begin = 0;
+        auto flush = [&](size_t end) {
+            if (end > begin) {
+                launch_adam(g->params + begin, g->grads + begin, g->adam_m + begin, g->adam_v + begin, (long long)(end - begin),
+                            g->dyn_dev, s);
+                g->launches++;
+            }
+        };
+        for (auto &Gq : g->groups)
+            if (adam_fused(g, Gq, adam)) {
+                flush(Gq.w1_off);
+                begin = Gq.w1_off + (size_t)Gq.Kl * Gq.F_j * g->d1;
+            }
+        flush(g->n_params);
+    }
+}
+
+}  // namespace
 
 extern "C" int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t batch_size, const int64_t *negatives,
                               int loss_kind, float margin, float neg_weight, float learning_rate, float dropout,
@@ -1767,29 +1896,18 @@ extern "C" int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t
     }
     cudaStream_t s = g->stream;
     ensure_batch_capacity(g, batch_size);
-    const int slot = g->ring_pos;
-    g->ring_pos = (g->ring_pos + 1) % dgn_graph::kRing;
-    CUDA_CHECK(cudaEventSynchronize(g->ring_ev[slot]));
-    memcpy(g->batch_host[slot], batch, (size_t)batch_size * 2 * sizeof(int));
-    CUDA_CHECK(cudaMemcpyAsync(g->batch_dev, g->batch_host[slot], (size_t)batch_size * 2 * sizeof(int), cudaMemcpyHostToDevice, s));
-    if (negatives) {
-        memcpy(g->neg_host[slot], negatives, (size_t)batch_size * sizeof(long long));
-        CUDA_CHECK(cudaMemcpyAsync(g->neg_dev, g->neg_host[slot], (size_t)batch_size * sizeof(long long), cudaMemcpyHostToDevice, s));
+
+    // ---- the per-step block: one pinned slot, one host-to-device copy
+    const int slot = begin_step(g, dropout, seed, step, 3);
+    unsigned char *host = g->step_host[slot];
+    StepDyn *h = reinterpret_cast<StepDyn *>(host);
+    if (apply_update) {
+        // TF 1.8 ApplyAdam: alpha = lr * sqrt(1 - beta2^t) / (1 - beta1^t), float32
+        h->alpha = learning_rate * sqrtf(1.f - g->b2p) / (1.f - g->b1p);
+        h->omb1 = 1.f - g->beta1, h->omb2 = 1.f - g->beta2, h->eps = g->eps;
     }
-    CUDA_CHECK(cudaEventRecord(g->ring_ev[slot], s));
-
-    StepDeps deps;
-    run_forward(g, dropout, seed, step, deps);
-
     {
-        for (int t = 0; t < g->n_types; ++t) consume(g, deps.Z[t], 0);
-        PhaseScope ph(g, "decode");
-        if (!g->dzq_clean)  // normally left clean by the previous step's conversion kernel
-            for (auto &T : g->types) CUDA_CHECK(cudaMemsetAsync(T.dZq, 0, panel_floats(1, T.n) * sizeof(long long), s));
-        g->dzq_clean = false;
-        if (g->n_params > g->dec_off)
-            CUDA_CHECK(cudaMemsetAsync(g->grads + g->dec_off, 0, (g->n_params - g->dec_off) * sizeof(float), s));
-        DecodeArgs a = {};
+        DecodeArgs &a = h->dec;
         a.Zi = g->types[G.i].Z, a.Zj = g->types[G.j].Z, a.dZi = g->types[G.i].dZq, a.dZj = g->types[G.j].dZq;
         a.n_i = G.n_i, a.n_j = G.n_j;
         a.batch = g->batch_dev, a.neg_in = negatives ? g->neg_dev : nullptr, a.neg_out = g->neg_out;
@@ -1802,55 +1920,71 @@ extern "C" int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t
         a.pos_out = g->pos_out, a.neg_score_out = g->negs_out, a.loss_out = g->loss_dev;
         a.seed_lo = (uint32_t)(seed & 0xffffffffu), a.seed_hi = (uint32_t)(seed >> 32), a.step = step, a.relation = (uint32_t)r;
         a.scratch = g->decode_scratch, a.ticket = g->decode_ticket;
-        launch_decode(a, s);
-        g->launches++;
-        if (g->n_types <= kMaxTypes) {
-            FixedBatch fb = {};
-            for (auto &T : g->types) fb.q[fb.count] = T.dZq, fb.out[fb.count] = T.dZ, fb.n[fb.count] = (size_t)panel_floats(1, T.n), fb.count++;
-            launch_fixed_to_float_clear(fb, s);
-            g->launches++;
-            g->dzq_clean = true;
-        } else {
-            for (auto &T : g->types) {
-                launch_fixed_to_float(T.dZq, T.dZ, panel_floats(1, T.n), s);
-                g->launches++;
+    }
+    if (negatives) memcpy(host + g->step_neg_off, negatives, (size_t)batch_size * sizeof(long long));
+    memcpy(host + g->step_batch_off, batch, (size_t)batch_size * 2 * sizeof(int));
+    commit_step(g, slot, g->step_batch_off + (size_t)batch_size * 2 * sizeof(int));
+
+    if (!g->dzq_clean)  // normally left clean by the previous step's conversion kernel
+        for (auto &T : g->types) CUDA_CHECK(cudaMemsetAsync(T.dZq, 0, panel_floats(1, T.n) * sizeof(long long), s));
+    AdamStep mode;
+    mode.alpha = apply_update ? 1.f : 0.f;
+    for (auto &Gq : g->groups) Gq.w1_grad_stale = !Gq.gen_feat && adam_fused(g, Gq, mode);
+
+    // ---- the step itself: a CUDA graph replay when this configuration has been seen before
+    bool done = false;
+    if (g->use_graphs && !g->timing) {
+        int parity = 0;
+        for (auto &Gq : g->groups)
+            if (Gq.partitioned)
+                for (int x = 0; x < 3; ++x) parity |= (int)(Gq.xch[x].stamp & 1u) << Gq.xch[x].id;
+        uint32_t rate_bits;
+        memcpy(&rate_bits, &dropout, sizeof(rate_bits));
+        dgn_graph::StepGraph &sg = g->step_graphs[std::make_tuple(rate_bits, apply_update ? 1 : 0, g->keep_grads ? 1 : 0, parity)];
+        if (sg.exec == nullptr && sg.seen++ >= 1) {
+            // second occurrence: capture (the first ran directly: lazy module loading and function attributes are done)
+            const long long before = g->launches;
+            cudaGraph_t graph = nullptr;
+            CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            g->capturing = true;
+            try {
+                issue_train_step(g, dropout, apply_update != 0);
+            } catch (...) {
+                g->capturing = false;
+                cudaStreamEndCapture(s, &graph);
+                if (graph) cudaGraphDestroy(graph);
+                throw;
+            }
+            g->capturing = false;
+            CUDA_CHECK(cudaStreamEndCapture(s, &graph));
+            sg.launches = g->launches - before;
+            g->launches = before;
+            cudaError_t e = cudaGraphInstantiate(&sg.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) {
+                sg.exec = nullptr;
+                DGN_FAIL(DGN_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
             }
         }
-        g->last_B = batch_size;
-        for (int t = 0; t < g->n_types; ++t) produced(g, deps.dZ[t], 0);
+        if (sg.exec != nullptr) {
+            CUDA_CHECK(cudaGraphLaunch(sg.exec, s));
+            g->launches += sg.launches;
+            g->graph_replays++;
+            done = true;
+        }
     }
-
-    AdamStep adam;
-    if (apply_update) {
-        // TF 1.8 ApplyAdam: alpha = lr * sqrt(1 - beta2^t) / (1 - beta1^t), float32
-        adam.alpha = learning_rate * sqrtf(1.f - g->b2p) / (1.f - g->b1p);
-        adam.omb1 = 1.f - g->beta1, adam.omb2 = 1.f - g->beta2, adam.eps = g->eps;
-    }
-    run_backward(g, dropout, deps, adam);
+    if (!done) issue_train_step(g, dropout, apply_update != 0);
+    g->dzq_clean = g->n_types <= kMaxTypes;
+    g->last_B = batch_size;
 
     if (apply_update) {
-        PhaseScope ph(g, "adam");
-        // every variable whose update was not fused into the kernel that produced its gradient
-        size_t begin = 0;
-        auto flush = [&](size_t end) {
-            if (end > begin) {
-                launch_adam(g->params + begin, g->grads + begin, g->adam_m + begin, g->adam_v + begin, (long long)(end - begin),
-                            adam.alpha, adam.omb1, adam.omb2, adam.eps, s);
-                g->launches++;
-            }
-        };
-        for (auto &Gq : g->groups)
-            if (adam_fused(g, Gq, adam)) {
-                flush(Gq.w1_off);
-                begin = Gq.w1_off + (size_t)Gq.Kl * Gq.F_j * g->d1;
-            }
-        flush(g->n_params);
         g->b1p *= g->beta1;
         g->b2p *= g->beta2;
     }
     if (loss_out) {
         CUDA_CHECK(cudaMemcpyAsync(g->loss_host, g->loss_dev, sizeof(float), cudaMemcpyDeviceToHost, s));
         CUDA_CHECK(cudaStreamSynchronize(s));
+        check_exchange(g);
         *loss_out = *g->loss_host;
     }
     DGN_API_END
@@ -2114,6 +2248,7 @@ extern "C" int dgn_sync(dgn_graph *g) {
     DGN_REQUIRE(g, "null graph");
     CUDA_CHECK(cudaSetDevice(g->device));
     CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    check_exchange(g);
     DGN_API_END
 }
 

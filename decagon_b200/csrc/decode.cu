@@ -51,7 +51,8 @@ __global__ void fixed_to_float_kernel(const long long *__restrict__ q, float *__
 
 // Grid of kDecodeCtas CTAs, each takes a contiguous slice of the batch (one warp per edge); the last CTA to
 // finish (ticket counter) adds the CTAs' loss and dM partials in CTA order, so the sums have a fixed order.
-__global__ void __launch_bounds__(kDecodeThreads, 1) decode_kernel(const DecodeArgs a) {
+__global__ void __launch_bounds__(kDecodeThreads, 1) decode_kernel(const StepDyn *__restrict__ dyn) {
+    const DecodeArgs a = dyn->dec;  // per-step arguments live in device memory (CUDA-graph replay)
     __shared__ float Ms[D][D + 1];
     __shared__ float dMs[D][D + 1];
     __shared__ float loss_w[kDecodeThreads / 32];
@@ -274,8 +275,8 @@ __global__ void relation_matrices_kernel(int decoder, const float *glb, const fl
 
 }  // namespace
 
-void launch_decode(const DecodeArgs &a, cudaStream_t s) {
-    decode_kernel<<<kDecodeCtas, kDecodeThreads, 0, s>>>(a);
+void launch_decode(const StepDyn *dyn, cudaStream_t s) {
+    decode_kernel<<<kDecodeCtas, kDecodeThreads, 0, s>>>(dyn);
     CUDA_CHECK(cudaGetLastError());
 }
 

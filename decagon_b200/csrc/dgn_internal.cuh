@@ -135,7 +135,7 @@ struct TaskArgs {
     // backward only: TF1 Adam applied to the rows as they are produced (out is then not written);
     // p / m / v have the layout of out
     float *adam_p, *adam_m, *adam_v;
-    float alpha, omb1, omb2, eps;
+    const struct StepDyn *dyn;  // Adam coefficients of the step (device memory)
 };
 
 struct EpiGroup {
@@ -221,6 +221,17 @@ struct DecodeArgs {
     unsigned *ticket;    // zero between launches
 };
 constexpr int kDecodeCtas = 16;
+constexpr int kMaxExchanges = 16;  // flag slots per source rank
+
+// Everything that changes from one training step to the next, in DEVICE memory: the kernels read it from here, so
+// the launches themselves are identical every step and the whole step can be replayed as one CUDA graph.  The host
+// fills a pinned copy and moves it (together with the batch) with ONE host-to-device copy per step.
+struct StepDyn {
+    uint32_t step, seed_lo, seed_hi, threshold;  // dropout streams: Philox key / counter words, keep threshold
+    float alpha, omb1, omb2, eps;                // TF1 Adam: alpha = lr sqrt(1 - b2^t) / (1 - b1^t)
+    uint32_t stamp[kMaxExchanges];               // multi-GPU: the stamp each exchange publishes / waits for this step
+    DecodeArgs dec;                              // minibatch, relation, decoder variables, loss
+};
 
 struct PredictArgs {
     const float *Zi, *Zj;
@@ -265,9 +276,9 @@ struct MaskBatch {  // layer-1 keep bits of up to kMaxMaskBatch groups, one laun
     long long n_words[kMaxMaskBatch], bits_per_rel[kMaxMaskBatch];
     const int *rel_ids[kMaxMaskBatch];
 };
-void launch_gen_mask_multi(const MaskBatch &mb, uint32_t stream_id, uint32_t step, uint64_t seed, uint32_t threshold, cudaStream_t s);
+void launch_gen_mask_multi(const MaskBatch &mb, uint32_t stream_id, const StepDyn *dyn, cudaStream_t s);
 void launch_gen_mask(uint32_t *words, long long n_words, long long bits_per_rel, int words_per_rel_or_0, const int *rel_ids,
-                     uint32_t stream_id, uint32_t step, uint64_t seed, uint32_t threshold, cudaStream_t s);
+                     uint32_t stream_id, const StepDyn *dyn, cudaStream_t s);
 int dense_row_block(int D1, int which);
 void launch_project(const DenseArgs &a, int D1, int D2, cudaStream_t s);
 void launch_dw2(const DenseArgs &a, int D1, int D2, cudaStream_t s);
@@ -279,7 +290,7 @@ int dense_tc_tiles(int n_j);
 void launch_project_tc(const DenseArgs &a, int D1, cudaStream_t s);
 void launch_dw2_tc(const DenseArgs &a, int D1, cudaStream_t s);
 void launch_dh_tc(const DenseArgs &a, int D1, cudaStream_t s);
-void launch_decode(const DecodeArgs &a, cudaStream_t s);
+void launch_decode(const StepDyn *dyn, cudaStream_t s);  // arguments: dyn->dec
 constexpr int kMaxTypes = 8;
 struct FixedBatch {
     int count;
@@ -301,14 +312,12 @@ void launch_rank(const float *scores, long long n, int *idx_in, float *sorted_sc
                  cudaStream_t s);
 void launch_auc(const float *scores, const unsigned char *labels, long long n, float *sorted_scores,
                 unsigned char *sorted_labels, void *tmp, size_t tmp_bytes, double *out, cudaStream_t s);
-void launch_adam(float *p, const float *g, float *m, float *v, long long n, float alpha, float one_minus_b1,
-                 float one_minus_b2, float eps, cudaStream_t s);
+void launch_adam(float *p, const float *g, float *m, float *v, long long n, const StepDyn *dyn, cudaStream_t s);
 // multi-GPU exchange (node.cu): ordered sum of the local partials into this rank's exchange buffer; then
 // "exchange x reached stamp" is stored into every peer's flag array and awaited from every peer
 void launch_publish(const float *partial, int n_chunks, size_t floats, float *out, cudaStream_t s);
-void launch_signal_wait(uint32_t *const *peer_flags_dev, uint32_t *my_flags, int rank, int world, int x, uint32_t stamp,
-                        cudaStream_t s);
-constexpr int kMaxExchanges = 16;  // flag slots per source rank
+void launch_signal_wait(uint32_t *const *peer_flags_dev, uint32_t *my_flags, int rank, int world, int x, const StepDyn *dyn,
+                        unsigned long long timeout_ns, int *error_flag, cudaStream_t s);
 void launch_relation_matrices(int decoder, const float *glb, const float *loc, float *glb_out, float *loc_out,
                               cudaStream_t s);
 

@@ -233,7 +233,7 @@ __device__ __forceinline__ void mask_word(long long w, uint32_t *__restrict__ wo
         if (u >= threshold) out |= 1u << b;
         if (++e == bits_per_rel) {
             e = 0, ++rel, cached_ctr = -1;
-            rid = (uint32_t)rel_ids[rel];  // rel_ids carries one spare entry past the last relation
+            rid = (uint32_t)rel_ids[rel];  // rel_ids carries 33 spare entries: a word spans at most 32 relation boundaries
         }
     }
     words[w] = out;
@@ -243,16 +243,17 @@ __device__ __forceinline__ void mask_word(long long w, uint32_t *__restrict__ wo
 // register slots to the L2-bound gather kernels of the other stream lane that run beside it.
 __global__ void __launch_bounds__(256) gen_mask_kernel(uint32_t *__restrict__ words, long long n_words, long long bits_per_rel,
                                                        int words_per_rel, const int *__restrict__ rel_ids, uint32_t stream_id,
-                                                       uint32_t step, uint32_t seed_lo, uint32_t seed_hi, uint32_t threshold,
-                                                       long long total_bits) {
+                                                       const StepDyn *__restrict__ dyn, long long total_bits) {
     const long long stride = (long long)gridDim.x * blockDim.x;
+    const uint32_t step = dyn->step, seed_lo = dyn->seed_lo, seed_hi = dyn->seed_hi, threshold = dyn->threshold;
     for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < n_words; w += stride)
         mask_word(w, words, bits_per_rel, words_per_rel, rel_ids, stream_id, step, seed_lo, seed_hi, threshold, total_bits);
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(float *__restrict__ p, const float *__restrict__ g,
                                                    float *__restrict__ m, float *__restrict__ v, long long n,
-                                                   float alpha, float omb1, float omb2, float eps) {
+                                                   const StepDyn *__restrict__ dyn) {
+    const float alpha = dyn->alpha, omb1 = dyn->omb1, omb2 = dyn->omb2, eps = dyn->eps;
     const long long n4 = n >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -294,15 +295,32 @@ __global__ void __launch_bounds__(256) publish_kernel(const float4 *__restrict__
 // One CTA, thread t talks to rank t.  The exchange buffer was written by the previous kernel of this
 // stream; peers read it through NVLink after they see the stamp.
 __global__ void signal_wait_kernel(uint32_t *const *__restrict__ peer_flags, uint32_t *my_flags, int rank, int world, int x,
-                                   uint32_t stamp) {
+                                   const StepDyn *__restrict__ dyn, unsigned long long timeout_ns, int *error_flag) {
     const int t = threadIdx.x;
     if (t >= world) return;
+    const uint32_t stamp = dyn->stamp[x];
     __threadfence_system();
     volatile uint32_t *dst = peer_flags[t] + rank * kMaxExchanges + x;
     *dst = stamp;
     volatile uint32_t *src = my_flags + t * kMaxExchanges + x;
-    for (long long spin = 0; (int)(*src - stamp) < 0; ++spin)
-        if (spin > (1ll << 28)) __trap();  // a lost peer must fault, not hang the GPU
+    // Ranks drift apart on the host (logging, evaluation on rank 0, a re-finalize): poll with a back-off and give
+    // up by WALL CLOCK, not by iteration count.  A peer that never arrives must not hang the GPU and must not kill
+    // the context either: the error flag is raised, the kernel returns and the host reports DGN_ERR_CUDA at its next
+    // synchronisation point (dgn_train_step with loss_out, dgn_sync).
+    unsigned long long t0 = 0;
+    unsigned ns = 32;
+    for (long long spin = 0; (int)(*src - stamp) < 0; ++spin) {
+        if (spin < 64) continue;
+        if (t0 == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        __nanosleep(ns);
+        if (ns < 2048) ns <<= 1;
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > timeout_ns) {
+            atomicExch(error_flag, 1 + t);
+            break;
+        }
+    }
     __threadfence_system();
 }
 
@@ -356,33 +374,33 @@ void launch_publish(const float *partial, int n_chunks, size_t floats, float *ou
     CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_signal_wait(uint32_t *const *peer_flags_dev, uint32_t *my_flags, int rank, int world, int x, uint32_t stamp,
-                        cudaStream_t s) {
-    signal_wait_kernel<<<1, 32, 0, s>>>(peer_flags_dev, my_flags, rank, world, x, stamp);
+void launch_signal_wait(uint32_t *const *peer_flags_dev, uint32_t *my_flags, int rank, int world, int x, const StepDyn *dyn,
+                        unsigned long long timeout_ns, int *error_flag, cudaStream_t s) {
+    signal_wait_kernel<<<1, 32, 0, s>>>(peer_flags_dev, my_flags, rank, world, x, dyn, timeout_ns, error_flag);
     CUDA_CHECK(cudaGetLastError());
 }
 
 // layer-1 keep bits (packed mode) of several groups in one launch: blockIdx.y = group
-__global__ void __launch_bounds__(256) gen_mask_multi_kernel(const MaskBatch mb, uint32_t stream_id, uint32_t step, uint32_t seed_lo,
-                                                             uint32_t seed_hi, uint32_t threshold) {
+__global__ void __launch_bounds__(256) gen_mask_multi_kernel(const MaskBatch mb, uint32_t stream_id, const StepDyn *__restrict__ dyn) {
     const int q = blockIdx.y;
+    const uint32_t step = dyn->step, seed_lo = dyn->seed_lo, seed_hi = dyn->seed_hi, threshold = dyn->threshold;
     const long long n_words = mb.n_words[q], stride = (long long)gridDim.x * blockDim.x;
     for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < n_words; w += stride)
         mask_word(w, mb.words[q], mb.bits_per_rel[q], 0, mb.rel_ids[q], stream_id, step, seed_lo, seed_hi, threshold, n_words * 32);
 }
 
-void launch_gen_mask_multi(const MaskBatch &mb, uint32_t stream_id, uint32_t step, uint64_t seed, uint32_t threshold, cudaStream_t s) {
+void launch_gen_mask_multi(const MaskBatch &mb, uint32_t stream_id, const StepDyn *dyn, cudaStream_t s) {
     if (mb.n == 0) return;
     long long most = 0;
     for (int q = 0; q < mb.n; ++q) most = std::max(most, mb.n_words[q]);
     if (most == 0) return;
     dim3 grid((unsigned)std::min<long long>((most + 255) / 256, 148 * 3), (unsigned)mb.n), block(256);
-    gen_mask_multi_kernel<<<grid, block, 0, s>>>(mb, stream_id, step, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), threshold);
+    gen_mask_multi_kernel<<<grid, block, 0, s>>>(mb, stream_id, dyn);
     CUDA_CHECK(cudaGetLastError());
 }
 
 void launch_gen_mask(uint32_t *words, long long n_words, long long bits_per_rel, int words_per_rel, const int *rel_ids,
-                     uint32_t stream_id, uint32_t step, uint64_t seed, uint32_t threshold, cudaStream_t s) {
+                     uint32_t stream_id, const StepDyn *dyn, cudaStream_t s) {
     if (n_words == 0) return;
     const long long total_bits = n_words * 32;  // packed mode: caller rounds the word count up
     static int ctas_per_sm = 0;  // DGN_MASK_CTAS: CTAs per SM the layer-2 mask kernel may occupy (default 3)
@@ -391,17 +409,14 @@ void launch_gen_mask(uint32_t *words, long long n_words, long long bits_per_rel,
         ctas_per_sm = e && atoi(e) > 0 ? atoi(e) : 3;
     }
     dim3 grid((unsigned)std::min<long long>((n_words + 255) / 256, 148LL * ctas_per_sm)), block(256);
-    gen_mask_kernel<<<grid, block, 0, s>>>(words, n_words, bits_per_rel, words_per_rel, rel_ids, stream_id, step,
-                                           (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), threshold,
-                                           total_bits);
+    gen_mask_kernel<<<grid, block, 0, s>>>(words, n_words, bits_per_rel, words_per_rel, rel_ids, stream_id, dyn, total_bits);
     CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_adam(float *p, const float *g, float *m, float *v, long long n, float alpha, float omb1, float omb2,
-                 float eps, cudaStream_t s) {
+void launch_adam(float *p, const float *g, float *m, float *v, long long n, const StepDyn *dyn, cudaStream_t s) {
     if (n == 0) return;
     dim3 grid(148 * 8), block(256);
-    adam_kernel<<<grid, block, 0, s>>>(p, g, m, v, n, alpha, omb1, omb2, eps);
+    adam_kernel<<<grid, block, 0, s>>>(p, g, m, v, n, dyn);
     CUDA_CHECK(cudaGetLastError());
 }
 

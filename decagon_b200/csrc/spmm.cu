@@ -530,6 +530,8 @@ __global__ void __launch_bounds__(kStagedThreads, 1) spmm_tstaged_kernel(const T
     __syncthreads();
     const unsigned char *xrow = smem_raw + (l8 << 4);
     const size_t out_rows = (size_t)a.K * a.n_out_rows;
+    float alpha = 0.f, omb1 = 0.f, omb2 = 0.f, eps = 0.f;
+    if (a.adam_p != nullptr) alpha = a.dyn->alpha, omb1 = a.dyn->omb1, omb2 = a.dyn->omb2, eps = a.dyn->eps;
 
     for (int t = 0; t < n_rel; ++t) {
         const int k = a.slot_rel[r_begin + t];
@@ -574,7 +576,7 @@ __global__ void __launch_bounds__(kStagedThreads, 1) spmm_tstaged_kernel(const T
                         float *pq = &P4.x, *mq = &M4.x, *vq = &V4.x;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            adam_update(pq[q], mq[q], vq[q], gg[q], a.alpha, a.omb1, a.omb2, a.eps);
+                            adam_update(pq[q], mq[q], vq[q], gg[q], alpha, omb1, omb2, eps);
                         }
                         *reinterpret_cast<float4 *>(a.adam_p + o) = P4;
                         *reinterpret_cast<float4 *>(a.adam_m + o) = M4;

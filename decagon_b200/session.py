@@ -162,9 +162,23 @@ class Session(object):
             if (int(self._fed(feed, opt.batch_row_edge_type)), int(self._fed(feed, opt.batch_col_edge_type))) != g:
                 raise ValueError('batch_row_edge_type / batch_col_edge_type do not match relation %d = %s' % (r, g))
             eng.keep_gradients('grad' in kinds)  # [opt_op, grads_vars]: no fused Adam, every gradient is stored
-            loss = eng.train_step(r, batch, negatives=None, loss=opt.loss_kind, margin=opt.margin,
-                                  neg_weight=opt.neg_sample_weights, lr=opt.learning_rate, dropout=dropout,
-                                  seed=self.seed, step=self.step, apply_update='opt_op' in kinds)
+            step_kw = dict(negatives=None, loss=opt.loss_kind, margin=opt.margin, neg_weight=opt.neg_sample_weights,
+                           lr=opt.learning_rate, dropout=dropout, seed=self.seed, step=self.step)
+            pair_scores = {}
+            if kinds & {'preds', 'neg_preds'}:
+                # batch_predict (optimizer.py:51,55,63-85): the full B x B matrices of the step's embeddings and
+                # PRE-update decoder variables -- only their diagonals enter the loss.  A debugging fetch, never on
+                # the training path: the step is first run without the update, the pairs are scored on the device,
+                # then (with opt_op) the identical step (same streams: same masks and negatives) applies the update.
+                loss = eng.train_step(r, batch, apply_update=False, **step_kw)
+                negs = eng.last_batch_outputs(opt.batch_size)[2]
+                B = opt.batch_size
+                for kind, rows in (('preds', batch[:, 0]), ('neg_preds', negs)):
+                    if kind in kinds:
+                        pairs = np.stack([np.repeat(rows, B), np.tile(batch[:, 1], B)], axis=1)
+                        pair_scores[kind] = eng.predict_edges(r, pairs, sigmoid=False).reshape(B, B)
+            if 'opt_op' in kinds or not pair_scores:
+                loss = eng.train_step(r, batch, apply_update='opt_op' in kinds, **step_kw)
             self.step += 1
         elif kinds & {'predictions', 'embeddings', 'hidden1', 'layer1_group', 'layer2_group', 'decoder_scores'}:
             eng.forward(dropout, self.seed, self.step)
@@ -186,15 +200,7 @@ class Session(object):
                     batch_out = eng.last_batch_outputs(opt.batch_size)
                 results[idx] = batch_out[{'outputs': 0, 'neg_outputs': 1, 'neg_samples': 2}[kind]]
             elif kind in ('preds', 'neg_preds'):
-                # batch_predict (optimizer.py:51,55,63-85): the full B x B matrix of the step's embeddings -- only
-                # its diagonal enters the loss; scored on the device pair by pair, never on the training path
-                if batch_out is None:
-                    batch_out = eng.last_batch_outputs(opt.batch_size)
-                batch = np.asarray(self._fed(feed, opt.inputs))
-                rows = batch[:, 0] if kind == 'preds' else batch_out[2]
-                pairs = np.stack([np.repeat(rows, opt.batch_size), np.tile(batch[:, 1], opt.batch_size)], axis=1)
-                r = int(self._fed(feed, opt.batch_edge_type_idx))
-                results[idx] = eng.predict_edges(r, pairs, sigmoid=False).reshape(opt.batch_size, opt.batch_size)
+                results[idx] = pair_scores[kind]
             elif kind in ('row_inputs', 'col_inputs'):
                 batch = np.asarray(self._fed(feed, opt.inputs))
                 results[idx] = batch[:, 0 if kind == 'row_inputs' else 1].astype(np.int32)

@@ -162,7 +162,7 @@ def init_params(graph, rng):
 
 
 def cast_params(p, dtype):
-    return {name: {g: np.asarray(a, dtype=dtype) for g, a in d.items()} for name, d in p.items()}
+    return {name: {g: np.array(a, dtype=dtype) for g, a in d.items()} for name, d in p.items()}  # always a copy
 
 
 def zeros_like_params(p):
@@ -245,8 +245,11 @@ def encoder_forward(graph, p, rate=0.0, masks=None):
     return acc, c
 
 
-def encoder_backward(graph, p, cache, dZ):
-    """Gradients of W1 / W2 given dL/dZ (SURVEY.md section 9 'Backward')."""
+def encoder_backward(graph, p, cache, dZ, relu_mask=None):
+    """Gradients of W1 / W2 given dL/dZ (SURVEY.md section 9 'Backward').  relu_mask[t] (bool [n_t, d1], optional):
+    the activation pattern to differentiate through instead of ``H > 0`` -- ReLU is not differentiable at 0, and a
+    float32 implementation may round a pre-activation of ~1e-9 to the other side than float64 does; a parity test
+    passes the pattern of the implementation under test after checking that it differs only at such entries."""
     scale, masks = cache['scale'], cache['masks']
     gW1 = {g: np.zeros_like(a) for g, a in p['W1'].items()}
     gW2 = {g: np.zeros_like(a) for g, a in p['W2'].items()}
@@ -265,7 +268,7 @@ def encoder_backward(graph, p, cache, dZ):
             dH[j] += back
     for g in graph.groups:
         i, j = g
-        dY = dH[i] * (cache['H'][i] > 0)
+        dY = dH[i] * ((cache['H'][i] > 0) if relu_mask is None else relu_mask[i])
         dS = _l2norm_bwd(cache['Y1'][g], cache['n1'][g], dY)
         for k in range(graph.K[g]):
             G = graph.adj[g][k].T @ dS
@@ -327,7 +330,7 @@ def decode_backward(graph, p, Z, g, k, rows, cols, negs, dpos, dneg):
 
 
 def train_step_grads(graph, p, g, k, batch, negs, rate=0.0, masks=None, loss_kind='hinge', margin=0.1,
-                     neg_weight=1.0):
+                     neg_weight=1.0, relu_mask=None, want_cache=False):
     """One ``session.run([opt_op, cost, ...])`` worth of forward + backward (no update).
     Returns (loss, pos, neg, grads, Z)."""
     Z, cache = encoder_forward(graph, p, rate, masks)
@@ -337,13 +340,15 @@ def train_step_grads(graph, p, g, k, batch, negs, rate=0.0, masks=None, loss_kin
     neg = batch_scores(graph, p, Z, g, k, negs, cols)
     loss, dpos, dneg = loss_and_dscores(pos, neg, loss_kind, margin, neg_weight)
     dZ, dec = decode_backward(graph, p, Z, g, k, rows, cols, negs, dpos, dneg)
-    gW1, gW2 = encoder_backward(graph, p, cache, dZ)
+    gW1, gW2 = encoder_backward(graph, p, cache, dZ, relu_mask)
     grads = zeros_like_params(p)
     grads['W1'], grads['W2'] = gW1, gW2
     if 'R' in dec:
         grads['R'][g] = dec['R']
     if 'D' in dec:
         grads['D'][g][k] = dec['D']
+    if want_cache:
+        return loss, pos, neg, grads, Z, cache
     return loss, pos, neg, grads, Z
 
 

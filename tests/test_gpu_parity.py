@@ -54,14 +54,33 @@ def check_forward(c, eng, rate, step):
     return Z
 
 
+def relu_pattern(c, eng, H_ref):
+    """The device's ReLU activation pattern (hidden1 > 0), after checking that it differs from the oracle's only
+    where the pre-activation is zero to rounding: ReLU has no derivative there and float32 / float64 may land on
+    different sides (seen at the config-#3 shape: 1.2 M pre-activations, a handful within 1e-9 of zero)."""
+    pattern = {}
+    for t, h in H_ref.items():
+        dev = eng.hidden1_of(t)
+        pattern[t] = dev > 0
+        flipped = pattern[t] != (h > 0)
+        if flipped.any():
+            tiny = 1e-6 * np.abs(h).max()
+            assert np.abs(h[flipped]).max() <= tiny and np.abs(dev[flipped]).max() <= tiny, ('relu pattern', t)
+            assert flipped.sum() <= 1e-4 * flipped.size
+    return pattern
+
+
 def check_grads(c, eng, r, batch, rate, step, loss_kind, negs=None):
     g, k = c.graph.flat[r]
     if negs is None:
         negs = O.sample_negatives(c.thresholds(r), len(batch), r, step, SEED)
     masks = O.masks_for(c.graph, rate, step, SEED)
-    loss, pos, neg, grads, Z = O.train_step_grads(c.graph, c.p64, g, k, batch, negs, rate, masks, loss_kind)
     got = eng.train_step(r, batch, negatives=negs, loss=loss_kind, dropout=rate, seed=SEED, step=step,
                          apply_update=False)
+    _, cache = O.encoder_forward(c.graph, c.p64, rate, masks)
+    pattern = relu_pattern(c, eng, cache['H'])
+    loss, pos, neg, grads, Z = O.train_step_grads(c.graph, c.p64, g, k, batch, negs, rate, masks, loss_kind,
+                                                  relu_mask=pattern)
     gpos, gneg, gsamples = eng.last_batch_outputs(len(batch))
     assert np.array_equal(gsamples, negs)
     assert_close(gpos, pos, TOL, 'outputs')
@@ -318,7 +337,7 @@ def test_general_sparse_features(graph_kind):
 
 
 @pytest.mark.parametrize('env', [{'DGN_SINGLE_STREAM': '1'}, {'DGN_PROJECT_SS': '1'}, {'DGN_FUSE_ADAM': '0'},
-                                 {'DGN_DISABLE_TSTAGED': '1'}, {'DGN_MASK_CTAS': '1'}])
+                                 {'DGN_DISABLE_TSTAGED': '1'}, {'DGN_MASK_CTAS': '1'}, {'DGN_CUDA_GRAPH': '0'}])
 def test_alternate_code_paths(env):
     """The switches that select the non-default kernels / schedules (one stream instead of the lanes + mask stream,
     the shared-memory projection instead of the tensor-memory one, unfused Adam, gather-path backward) give the
@@ -341,7 +360,7 @@ def test_alternate_code_paths(env):
             adam.apply(p, grads)
             eng.train_step(r, batch, negatives=negs, seed=SEED, step=step, dropout=0.1, apply_update=True)
         now = eng.get_params()
-        for name in ('W2', 'R', 'D'):
+        for name in ('W1', 'W2', 'R', 'D'):
             for gg in now[name]:
                 assert rel_err(now[name][gg], p[name][gg]) <= 1e-4, (env, name, gg)
         eng.close()
@@ -373,7 +392,7 @@ def test_fused_adam_updates_w1_like_tf1():
         del os.environ['DGN_FUSE_ADAM']
     for e in (fused, keep, unfused):
         e.reset_optimizer()
-    p = O.cast_params(fused.get_params(), np.float32)
+    p = fused.get_params()
     adam = O.AdamTF1(p, lr=1e-3)
     for step, (r, batch) in enumerate(c.batches(3)):
         negs = O.sample_negatives(c.thresholds(r), len(batch), r, step, SEED)
@@ -439,7 +458,7 @@ def test_config3_fused_adam(poly):
     kw = dict(negatives=negs, seed=SEED, step=7, dropout=0.1)
     eng.train_step(r, batch, apply_update=False, **kw)
     grads = eng.get_grads()
-    p = O.cast_params(c.p32, np.float32)
+    p = {name: {g: a.copy() for g, a in d.items()} for name, d in c.p32.items()}  # cast_params would alias c.p32
     O.AdamTF1(p, lr=1e-3).apply(p, grads)
     eng.train_step(r, batch, apply_update=True, **kw)
     now = eng.get_params()
@@ -469,3 +488,33 @@ def test_config3_all_pairs(poly):
         out = buf.cpu().numpy()
         for q in range(4):
             assert_close(out[q], O.predict_all_pairs(c.graph, c.p64, Z, g, k0 + q), TOL, (g, k0 + q))
+
+
+def test_cuda_graph_replay_is_bit_identical():
+    """The training step replayed as ONE CUDA graph (default from the second step of a configuration on; per-step
+    values -- batch, relation, decoder pointers, dropout stream words, Adam coefficients -- come from the device
+    block StepDyn) against the same steps issued kernel by kernel (DGN_CUDA_GRAPH=0): losses, negatives and every
+    parameter bit for bit over steps that change relation group, dropout rate and update mode."""
+    c = Case(common.mini_poly(n_types=10, seed=31), batch_size=64)
+    graphed = c.engine()
+    os.environ['DGN_CUDA_GRAPH'] = '0'
+    try:
+        direct = c.engine()
+    finally:
+        del os.environ['DGN_CUDA_GRAPH']
+    for e in (graphed, direct):
+        e.reset_optimizer()
+    plan = [(0.1, True)] * 6 + [(0.0, True)] * 3 + [(0.1, False)] * 3 + [(0.1, True)] * 4
+    for step, ((r, batch), (rate, update)) in enumerate(zip(c.batches(len(plan)), plan)):
+        out = []
+        for e in (graphed, direct):
+            loss = e.train_step(r, batch, negatives=None, seed=SEED, step=step, dropout=rate, apply_update=update)
+            out.append((np.float32(loss), e.last_batch_outputs(len(batch))))
+        assert out[0][0] == out[1][0], (step, out[0][0], out[1][0])
+        for a, b in zip(out[0][1], out[1][1]):
+            assert np.array_equal(a, b), step
+    assert _same(graphed.get_params(), direct.get_params())
+    for t in c.graph.n_nodes:
+        assert np.array_equal(graphed.embeddings(t), direct.embeddings(t))
+    graphed.close()
+    direct.close()
