@@ -85,10 +85,18 @@ def assemble(gene_adj, gene_drug_adj, drug_drug_adj_list, decoders=None, transpo
 
 def toy_graph(decoders=None, seed=0, features=None):
     """Config #1.  ``np.random.seed(seed)`` then the draws of ``main.py:134-156``."""
+    return dummy_graph(500, 400, 3, decoders, seed, features)
+
+
+def dummy_graph(n_genes=200, n_drugs=250, n_types=3, decoders=None, seed=0, features=None):
+    """The reference's dummy-data generator (``DecagonDummyDataAdjacencyMatricesBuilder.py:36-67``; the same
+    algorithm as ``main.py:134-156``): planted-partition PPI graph of ``n_genes // 10`` groups of 10, gene-drug
+    edges where ``10 * randn > 15``, drug-drug relation t = pairs sharing exactly ``t + 4`` targets.  The defaults
+    are ``NumProteins`` / ``NumDrugs`` / ``NumDrugDrugRelationTypes`` of the reference's ``configuration.json:6-8``
+    (the run that produced ``decagon_iteration_results_0.csv``)."""
     import networkx as nx
     np.random.seed(seed)
-    n_genes, n_drugs, n_types = 500, 400, 3
-    gene_net = nx.planted_partition_graph(50, 10, 0.2, 0.05, seed=42)
+    gene_net = nx.planted_partition_graph(n_genes // 10, 10, 0.2, 0.05, seed=42)
     gene_adj = sp.csr_matrix(nx.adjacency_matrix(gene_net))
     gene_drug_adj = sp.csr_matrix((10 * np.random.randn(n_genes, n_drugs) > 15).astype(int))
     shared = (gene_drug_adj.T @ gene_drug_adj).toarray()

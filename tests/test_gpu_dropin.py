@@ -428,3 +428,57 @@ def test_feed_dict_token_skips_the_tuple_walk():
     assert len(walked) >= sum(inputs.edge_types.values())
     plain = dict(minibatch.update_feed_dict(minibatch.next_minibatch_feed_dict(placeholders), 0.1, placeholders))
     sess.run([opt.opt_op, opt.cost], feed_dict=plain)   # plain dicts keep working (slow path)
+
+
+def test_learning_curve_matches_the_reference_run():
+    """The only training artefact the reference ships: ``decagon_iteration_results_0.csv`` (rows 2-59), the log of
+    its trainer on the dummy data set of ``configuration.json:6-8,14-26`` (200 proteins, 250 drugs, 3 drug-drug
+    types + transposes; bilinear / dedicom decoders, hidden 64 / 32, batch 512, dropout 0.1, lr 1e-3, margin 0.1,
+    50 epochs of 24 iterations = 1200 iterations; the AUROC denominators 110 x 110 in the file fix the graph size).
+    It records the minibatch loss of edge type 0 = (0,0,0) falling from 47.9 (iteration 24) to 12.9 (iteration 1200)
+    and the validation AUROC of that edge type rising from 0.61 to 0.81.  TensorFlow's dropout / sampler streams
+    are unseeded, so the trajectory can only be matched as a band: the same trainer loop (DecagonTrainer.py:52-100)
+    through the drop-in classes must start in 45-52, end <= 16 and reach AUROC >= 0.76."""
+    from sklearn import metrics
+    from decagon_b200.evaluator import sigmoid
+    inputs = datasets.dummy_graph(200, 250, 3)
+    placeholders, minibatch, model, opt = build_trainable(inputs, batch_size=512)
+    sess = tf.Session(seed=SEED)
+    sess.run(tf.global_variables_initializer())
+    np.random.seed(0)
+    type0, itr, epochs = [], 0, 0
+    while itr < 1200:
+        minibatch.shuffle()
+        epochs += 1
+        while not minibatch.end() and itr < 1200:
+            fd = minibatch.update_feed_dict(minibatch.next_minibatch_feed_dict(placeholders), 0.1, placeholders)
+            _, cost, idx = sess.run([opt.opt_op, opt.cost, opt.batch_edge_type_idx], feed_dict=fd)
+            itr += 1
+            if int(idx) == 0:
+                type0.append((itr, float(cost)))
+    first = np.mean([c for i, c in type0 if i <= 24])
+    last = np.mean([c for i, c in type0 if i > 1200 - 48])
+    # validation AUROC of (0,0,0) as DecagonAccuracyEvaluator computes it (sigmoid of predictions at the edges),
+    # positives = val_edges, negatives = as many uniformly drawn non-edges (the fork that wrote the file drew 110)
+    rel = (0, 0, 0)
+    fd[placeholders['dropout']] = 0
+    fd[placeholders['batch_edge_type_idx']] = minibatch.edge_type2idx[rel]
+    fd[placeholders['batch_row_edge_type']], fd[placeholders['batch_col_edge_type']] = 0, 0
+    pred = sigmoid(sess.run(opt.predictions, feed_dict=fd))
+    pos = np.asarray(minibatch.val_edges[0, 0][0])
+    dense = inputs.adj_mats[0, 0][0].toarray()
+    rng = np.random.RandomState(1)
+    neg = []
+    while len(neg) < len(pos):
+        u, v = rng.randint(0, 200, 2)
+        if u != v and dense[u, v] == 0:
+            neg.append((u, v))
+    neg = np.asarray(neg)
+    scores = np.concatenate([pred[pos[:, 0], pos[:, 1]], pred[neg[:, 0], neg[:, 1]]])
+    labels = np.concatenate([np.ones(len(pos)), np.zeros(len(neg))])
+    auroc = metrics.roc_auc_score(labels, scores)
+    print('learning curve: %d epochs, edge-type-0 loss %.2f -> %.2f (reference 47.94 -> 12.92), AUROC %.3f (reference 0.814)'
+          % (epochs, first, last, auroc))
+    assert 45.0 <= first <= 52.0, first
+    assert last <= 16.0, last
+    assert auroc >= 0.76, auroc
