@@ -69,6 +69,7 @@ SIGNATURES = {
     'dgn_timeline_get': (ctypes.c_int, [c_graph, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
                                         c_f64p, c_f64p]),
     'dgn_launch_count': (ctypes.c_int, [c_graph, c_i64p]),
+    'dgn_counters': (ctypes.c_int, [c_graph, c_i64p, c_i64p]),
     'dgn_timer_start': (ctypes.c_int, [c_graph]),
     'dgn_timer_stop': (ctypes.c_int, [c_graph, c_f64p]),
     'dgn_memory_bytes': (ctypes.c_int, [c_graph, c_i64p, c_i64p]),

@@ -8,6 +8,7 @@ descending.  Here the candidates are scored and sorted on the device (``dgn_rank
 no host argsort over every remaining possibility.
 """
 import numpy as np
+import scipy.sparse as sp
 
 
 def num_to_unmask(data_set_size, num_iters):
@@ -43,3 +44,46 @@ class GreedyCandidateRanker(object):
             masks[rel][row, col] = 1
         self.possibilities = np.delete(self.possibilities, idxs, axis=0)
         return masks
+
+
+class SparseRelationMasks(object):
+    """``RandomMaskingActiveLearner.adjMtxMasks`` + ``_applyMask`` (``RandomMaskingActiveLearner.py:24-27,173-200``)
+    without the dense arrays: the reference keeps one dense ``n x n`` float mask per relation (964 x 645^2 x 8 B =
+    3.2 GB at the polypharmacy shape) and multiplies it into ``mtx.toarray()`` every round, although a mask entry
+    only matters where the adjacency is non-zero.  Here a relation is its canonical CSR plus ONE keep bit per
+    non-zero; ``unmask`` looks the coordinates up with a sorted search, ``apply`` returns exactly the matrices
+    ``RelationCsrMatrix(np.multiply(mask, mtx.toarray()))`` would hold.  Feeding the resulting tuples re-uploads
+    only the drug-drug group: ``dgn_graph_finalize`` rebuilds the groups whose relations changed and nothing else."""
+
+    def __init__(self, matrices):
+        self.full, self.keep, self._lin = {}, {}, {}
+        for rel, m in matrices.items():
+            m = sp.csr_matrix(m).copy()
+            m.eliminate_zeros()
+            m.sort_indices()
+            self.full[rel] = m
+            self.keep[rel] = np.zeros(m.nnz, dtype=bool)
+            rows = np.repeat(np.arange(m.shape[0], dtype=np.int64), np.diff(m.indptr))
+            self._lin[rel] = rows * m.shape[1] + m.indices
+
+    def unmask(self, coords):
+        """``coords``: int ``[n, 3]`` rows ``(relation id, row, col)`` (``self.possibilities[idxsToUnmask]``)."""
+        coords = np.asarray(coords).reshape(-1, 3)
+        for rel in np.unique(coords[:, 0]):
+            sel = coords[coords[:, 0] == rel]
+            lin = sel[:, 1].astype(np.int64) * self.full[rel].shape[1] + sel[:, 2]
+            nz = self._lin[rel]
+            pos = np.searchsorted(nz, lin)
+            hit = (pos < len(nz)) & (nz[np.minimum(pos, len(nz) - 1)] == lin) if len(nz) else np.zeros(len(lin), bool)
+            self.keep[rel][pos[hit]] = True
+
+    def apply(self):
+        """{relation id: csr} of the un-masked part of every relation."""
+        out = {}
+        for rel, m in self.full.items():
+            k = self.keep[rel]
+            counts = np.add.reduceat(k.astype(np.int64), m.indptr[:-1]) if m.nnz else np.zeros(m.shape[0], np.int64)
+            counts[np.diff(m.indptr) == 0] = 0
+            indptr = np.concatenate([[0], np.cumsum(counts)]).astype(m.indptr.dtype)
+            out[rel] = sp.csr_matrix((m.data[k], m.indices[k], indptr), shape=m.shape)
+        return out

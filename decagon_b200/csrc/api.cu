@@ -337,6 +337,7 @@ struct Group {
     DevCsr relcsr, fwd, bwd;
     SegTable fwd_seg, bwd_seg;
     bool staged = false;
+    bool dirty = true;  // a relation / the features / the partition changed since the device structures were built
     int lane = 0;
     SlotTable slots1, slots2;
     int staged_version = 3;      // 2: spmm_staged_kernel, 3: spmm_staged3_kernel (position order, mbarrier pipeline)
@@ -424,6 +425,7 @@ struct dgn_graph {
     bool use_graphs = true;   // DGN_CUDA_GRAPH=0: issue every kernel from the host each step
     bool capturing = false;
     long long graph_replays = 0;
+    long long groups_rebuilt = 0;  // build_group calls so far (tests: incremental finalize)
     float *pos_out = nullptr, *negs_out = nullptr, *loss_dev = nullptr, *loss_host = nullptr;
     float *decode_scratch = nullptr;
     unsigned *decode_ticket = nullptr;
@@ -1529,6 +1531,7 @@ extern "C" int dgn_graph_set_relation(dgn_graph *g, int r, int32_t n_rows, int32
                 n_cols, G.i, G.j, G.n_i, G.n_j);
     csr_from_coo(n_rows, n_cols, nnz, coo_rows, coo_cols, vals, G.rel[g->flat[r].second]);
     G.rel_set[g->flat[r].second] = true;
+    G.dirty = true;  // only this group's device structures are rebuilt by the next dgn_graph_finalize
     g->finalized = false;
     DGN_API_END
 }
@@ -1550,6 +1553,8 @@ extern "C" int dgn_graph_set_features(dgn_graph *g, int type, int32_t n_rows, in
     T.feat = HostCsr();
     if (!identity) csr_from_coo(n_rows, n_cols, nnz, coo_rows, coo_cols, vals, T.feat);  // canonical (row, col) order
     T.feat_set = true;
+    for (auto &G : g->groups)
+        if (G.j == type) G.dirty = true;
     g->finalized = false;
     DGN_API_END
 }
@@ -1615,10 +1620,19 @@ extern "C" int dgn_graph_finalize(dgn_graph *g) {
             loc.resize(G.K);
             std::iota(loc.begin(), loc.end(), 0);
         }
+        if (loc != G.loc) G.dirty = true;
         set_local_relations(G, loc);
     }
     layout_arena(g);
-    for (auto &G : g->groups) build_group(g, G);
+    // incremental: only the groups whose relations (or features, or partition) changed are rebuilt -- an
+    // active-learning round that re-masks the drug-drug relations (RandomMaskingActiveLearner._applyMask,
+    // RandomMaskingActiveLearner.py:184-200) leaves the protein-protein structures on the device untouched
+    for (auto &G : g->groups)
+        if (G.dirty) {
+            build_group(g, G);
+            G.dirty = false;
+            g->groups_rebuilt++;
+        }
     build_comm(g);
     // no device allocation may happen while a peer waits for this rank inside an exchange: take the batch
     // buffers now (a larger batch later re-allocates; keep the ranks in step around such a change)
@@ -1782,6 +1796,7 @@ extern "C" int dgn_comm_init(dgn_graph *g, int rank, int world) {
     CUDA_CHECK(cudaSetDevice(g->device));
     CUDA_CHECK(cudaStreamSynchronize(g->stream));
     g->rank = rank, g->world = world;
+    for (auto &G : g->groups) G.dirty = true;
     g->finalized = false;
     if (world > 1) free_arena(g);  // the layout depends on the partition, which needs the relations: see finalize
     DGN_API_END
@@ -2307,6 +2322,14 @@ extern "C" int dgn_timeline_get(dgn_graph *g, int index, char *name_out, int nam
     CUDA_CHECK(cudaEventElapsedTime(&b, g->phases[0].start, p.stop));
     snprintf(name_out, (size_t)name_cap, "%s", p.name.c_str());
     *lane_out = p.lane, *start_ms_out = a, *stop_ms_out = b;
+    DGN_API_END
+}
+
+extern "C" int dgn_counters(dgn_graph *g, int64_t *graph_replays_out, int64_t *groups_rebuilt_out) {
+    DGN_API_BEGIN
+    DGN_REQUIRE(g, "null graph");
+    if (graph_replays_out) *graph_replays_out = g->graph_replays;
+    if (groups_rebuilt_out) *groups_rebuilt_out = g->groups_rebuilt;
     DGN_API_END
 }
 

@@ -345,6 +345,12 @@ class Engine(object):
         check(self.lib.dgn_launch_count(self._h, ctypes.byref(n)))
         return n.value
 
+    def counters(self):
+        """(training steps replayed as one CUDA graph, groups built by finalize so far)."""
+        a, b = ctypes.c_int64(0), ctypes.c_int64(0)
+        check(self.lib.dgn_counters(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
     def timer_start(self):
         check(self.lib.dgn_timer_start(self._h))
 

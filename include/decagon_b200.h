@@ -222,6 +222,12 @@ int dgn_timing_enable(dgn_graph *g, int enable);
 int dgn_timing_reset(dgn_graph *g);
 int dgn_timing_get(dgn_graph *g, const char *name, double *ms_out, int64_t *count_out);
 int dgn_launch_count(dgn_graph *g, int64_t *launches_out);
+/* graph_replays: training steps executed as ONE CUDA-graph launch (from the second step of a configuration on; the
+ * kernels inside still count in dgn_launch_count); groups_rebuilt: how many (i, j) groups dgn_graph_finalize has
+ * built so far -- a finalize after dgn_graph_set_relation rebuilds only the groups whose relations changed (the
+ * active-learning rounds of RandomMaskingActiveLearner.py:150-200 re-mask the drug-drug relations only).  Either
+ * pointer may be NULL. */
+int dgn_counters(dgn_graph *g, int64_t *graph_replays_out, int64_t *groups_rebuilt_out);
 /* recorded phase `index` (0 .. until DGN_ERR_INVALID): name, stream lane, start / stop in ms after the first
  * recorded phase began -- a timeline of one step across the two lanes (tools/timeline.py) */
 int dgn_timeline_get(dgn_graph *g, int index, char *name_out, int name_cap, int *lane_out, double *start_ms_out,

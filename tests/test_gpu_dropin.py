@@ -482,3 +482,45 @@ def test_learning_curve_matches_the_reference_run():
     assert 45.0 <= first <= 52.0, first
     assert last <= 16.0, last
     assert auroc >= 0.76, auroc
+
+
+def test_remasked_relations_rebuild_only_their_group():
+    """An active-learning round (RandomMaskingActiveLearner.getUpdate, RandomMaskingActiveLearner.py:150-200) changes
+    the drug-drug adjacency only.  Re-feeding those relations rebuilds ONE group on the device (the protein-protein
+    structures stay), and the result equals an engine built from scratch on the new graph."""
+    from decagon_b200.active_learning import SparseRelationMasks
+    case = common.Case(datasets.toy_graph())
+    eng = case.engine()
+    _, built0 = eng.counters()
+    assert built0 == 4
+    # un-mask half of the non-zeros of every drug-drug relation, re-normalise like the iterator does, re-feed
+    dd = {k: m for k, m in enumerate(case.inputs.adj_mats[1, 1])}
+    masks = SparseRelationMasks(dd)
+    rng = np.random.RandomState(0)
+    for k, m in dd.items():
+        coo = m.tocoo()
+        pick = rng.rand(coo.nnz) < 0.5
+        masks.unmask(np.column_stack([np.full(pick.sum(), k), coo.row[pick], coo.col[pick]]))
+    new = masks.apply()
+    fresh = common.Case(datasets.toy_graph())
+    for k in dd:
+        tup = case.it.preprocess_graph(new[k])
+        r = case.it.edge_type2idx[1, 1, k]
+        eng.set_relation(r, *tup)
+        fresh.it.adj_train[1, 1][k] = tup
+    eng.finalize()
+    assert eng.counters()[1] == built0 + 1
+    ref = fresh.engine()
+    for e in (eng, ref):
+        e.set_params(case.p32)
+        e.forward(0.1, SEED, 4)
+    for t in case.graph.n_nodes:
+        assert np.array_equal(eng.embeddings(t), ref.embeddings(t))
+    r, batch = case.batches(4)[3]
+    for e in (eng, ref):
+        e.reset_optimizer()
+        e.train_step(r, batch, dropout=0.1, seed=SEED, step=0)
+    a, b = eng.get_params(), ref.get_params()
+    assert all(np.array_equal(a[n][g], b[n][g]) for n in a for g in a[n])
+    eng.close()
+    ref.close()

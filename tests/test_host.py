@@ -316,3 +316,32 @@ def test_multi_hot_features_and_unmask_schedule():
     # 1 %, 1 %, 2 %, 4 %, ... of the data set, capped at 100 % in total
     sizes = [num_to_unmask(10000, i) for i in range(8)]
     assert sizes == [100, 100, 200, 400, 800, 1600, 3200, 3600] and sum(sizes) == 10000
+
+
+def test_sparse_relation_masks_equal_the_dense_reference_formula():
+    """RandomMaskingActiveLearner._updateMask / _applyMask (RandomMaskingActiveLearner.py:166-200) keep dense n x n
+    masks and multiply them into mtx.toarray(); SparseRelationMasks keeps one bit per non-zero.  Same matrices."""
+    import scipy.sparse as sp
+    from decagon_b200.active_learning import SparseRelationMasks
+    rng = np.random.RandomState(0)
+    n = 60
+    mats = {}
+    for rel in (3, 7, 11):
+        a = (rng.rand(n, n) < 0.08).astype(np.float64)
+        a[5] = 0  # an empty row
+        mats[rel] = sp.csr_matrix(np.maximum(a, a.T))
+    grid = np.array([(rel, r, c) for rel in mats for r in range(n) for c in range(n)])
+    dense_masks = {rel: np.zeros((n, n)) for rel in mats}
+    sparse = SparseRelationMasks(mats)
+    remaining = grid
+    for round_ in range(4):
+        pick = rng.choice(len(remaining), size=len(remaining) // 5, replace=False)
+        for rel, r, c in remaining[pick]:               # the reference's loop (:173-174)
+            dense_masks[rel][r, c] = 1
+        sparse.unmask(remaining[pick])
+        remaining = np.delete(remaining, pick, axis=0)
+        got = sparse.apply()
+        for rel in mats:
+            want = sp.csr_matrix(np.multiply(dense_masks[rel], mats[rel].toarray()))   # _applyMask (:187-190)
+            assert (got[rel] != want).nnz == 0 and got[rel].nnz == want.nnz
+            assert np.array_equal(got[rel].indptr, want.indptr) and np.array_equal(got[rel].indices, want.indices)
