@@ -380,7 +380,11 @@ struct dgn_graph {
     bool allow_staged = true, allow_tstaged = true;
     int staged_version = 3;
     cudaStream_t stream = nullptr;   // lane 0: groups of many small relations (staged kernels), decode, Adam
-    cudaStream_t stream2 = nullptr;  // lane 1: the other groups; ordered against lane 0 by events per tensor
+    // lanes 1 .. kMaxLanes - 1: the other groups, ONE LANE PER GROUP (their short, latency-bound kernels overlap each
+    // other); ordered against lane 0 and against each other by events per tensor
+    static const int kMaxLanes = 5;
+    cudaStream_t side[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // side[0] unused
+    int n_lanes = 2;
     cudaStream_t stream3 = nullptr;  // layer-2 keep words of every group (integer ALU work beside lane 1's gathers)
     cudaEvent_t mask_go = nullptr, mask_done = nullptr;
     bool own_stream = false;
@@ -445,7 +449,7 @@ struct PhaseScope {
     cudaEvent_t stop = nullptr;
     cudaStream_t st;
     PhaseScope(dgn_graph *g_, const char *name, int group = -1, int lane = 0) : g(g_) {
-        st = lane == 1 && g->stream2 ? g->stream2 : g->stream;
+        st = lane >= 1 && g->two_lanes && g->side[lane] ? g->side[lane] : g->stream;
         if (!g->timing) return;
         Phase p;
         p.name = name;
@@ -462,7 +466,7 @@ struct PhaseScope {
     }
 };
 
-cudaStream_t lane_stream(dgn_graph *g, int lane) { return lane == 1 && g->two_lanes ? g->stream2 : g->stream; }
+cudaStream_t lane_stream(dgn_graph *g, int lane) { return lane >= 1 && g->two_lanes ? g->side[lane] : g->stream; }
 // the tensor was just written on `lane`
 void produced(dgn_graph *g, Dep &d, int lane) {
     if (!g->two_lanes) return;
@@ -480,16 +484,22 @@ void consume(dgn_graph *g, const Dep &d, int lane) {
     if (!g->two_lanes || d.ev == nullptr || d.lane == lane) return;
     CUDA_CHECK(cudaStreamWaitEvent(lane_stream(g, lane), d.ev, 0));
 }
-// lane 0 continues after everything queued on lane 1 (and vice versa when both)
-void join_lanes(dgn_graph *g, bool both) {
+// every side lane continues after what is queued on lane 0
+void fork_lanes(dgn_graph *g) {
     if (!g->two_lanes) return;
     Dep d;
-    produced(g, d, 1);
-    consume(g, d, 0);
-    if (both) {
-        produced(g, d, 0);
-        consume(g, d, 1);
+    produced(g, d, 0);
+    for (int lane = 1; lane < g->n_lanes; ++lane) consume(g, d, lane);
+}
+// lane 0 continues after everything queued on the side lanes (and vice versa when both)
+void join_lanes(dgn_graph *g, bool both) {
+    if (!g->two_lanes) return;
+    for (int lane = 1; lane < g->n_lanes; ++lane) {
+        Dep d;
+        produced(g, d, lane);
+        consume(g, d, 0);
     }
+    if (both) fork_lanes(g);
 }
 
 size_t panel_floats(int P, long long rows) { return (size_t)P * (size_t)rows * 32; }
@@ -746,7 +756,7 @@ std::vector<int> lane_order(dgn_graph *g, bool by_col_type) {
     for (int pass = 0; pass < 2; ++pass)
         for (int gi = 0; gi < g->n_groups; ++gi) {
             const Group &G = g->groups[gi];
-            if (G.lane != 1) continue;
+            if (G.lane == 0) continue;
             const int t = by_col_type ? G.j : G.i;
             if ((g->types[t].lane == 0) == (pass == 0)) order.push_back(gi);
         }
@@ -767,11 +777,8 @@ void run_forward(dgn_graph *g, float rate, StepDeps &D) {
     D.S1.assign(g->n_groups, Dep()), D.S2.assign(g->n_groups, Dep()), D.dH.assign(g->n_groups, Dep());
     D.H.assign(g->n_types, Dep()), D.Z.assign(g->n_types, Dep()), D.dZ.assign(g->n_types, Dep()), D.dA.assign(g->n_types, Dep());
     g->dep_next = 0;
-    if (g->two_lanes) {  // lane 1 starts after everything queued so far (previous step's Adam, the per-step block)
-        Dep d;           // (every call ends with lane 1 joined into lane 0, so nothing is pending there)
-        produced(g, d, 0);
-        consume(g, d, 1);
-    }
+    fork_lanes(g);  // the side lanes start after everything queued so far (previous step's Adam, the per-step block);
+                    // every call ends with them joined into lane 0, so nothing is pending there
     if (drop) {
         if (g->two_lanes) {
             CUDA_CHECK(cudaEventRecord(g->mask_go, g->stream));  // after the join: last step's readers of mask2 are done
@@ -802,9 +809,7 @@ void run_forward(dgn_graph *g, float rate, StepDeps &D) {
             flush();
         }
         if (g->two_lanes) {
-            Dep d;
-            produced(g, d, 0);
-            consume(g, d, 1);
+            fork_lanes(g);  // the layer-1 keep bits of every group were drawn on lane 0
         } else {
             for (auto &G : g->groups) {
                 launch_gen_mask(G.mask2, G.mask2_words, (long long)G.n_j * g->d1, G.n_j * P1, G.rel_ids, kStreamDropout2, g->dyn_dev,
@@ -813,7 +818,8 @@ void run_forward(dgn_graph *g, float rate, StepDeps &D) {
             }
         }
     }
-    bool mask_waited[2] = {!(drop && g->two_lanes), !(drop && g->two_lanes)};
+    bool mask_waited[dgn_graph::kMaxLanes];
+    for (bool &w : mask_waited) w = !(drop && g->two_lanes);
     auto wait_mask2 = [&](int lane) {
         if (mask_waited[lane]) return;
         CUDA_CHECK(cudaStreamWaitEvent(lane_stream(g, lane), g->mask_done, 0));
@@ -888,14 +894,14 @@ void run_forward(dgn_graph *g, float rate, StepDeps &D) {
     {
         const std::vector<int> lo = lane_order(g, false);
         for (int gi : lo)
-            if (g->groups[gi].lane == 1) order.push_back(gi);
+            if (g->groups[gi].lane != 0) order.push_back(gi);
         for (int gi : lo)
             if (g->groups[gi].lane == 0) order.push_back(gi);
     }
     auto gate = [&](Group &G, std::vector<Dep> &deps) {  // lane 0 waits for every lane-1 group's partial sums
         if (G.lane != 0 || !G.staged) return;
         for (int q = 0; q < g->n_groups; ++q)
-            if (g->groups[q].lane == 1) consume(g, deps[q], 0);
+            if (g->groups[q].lane != 0) consume(g, deps[q], 0);
         wait_mask2(0);  // or the staged kernel would starve the mask generation as well
     };
     for (int gi : order) {
@@ -919,7 +925,7 @@ void run_forward(dgn_graph *g, float rate, StepDeps &D) {
         }
         produced(g, D.S1[gi], G.lane);
     }
-    for (int lane = 0; lane < 2; ++lane)
+    for (int lane = 0; lane < dgn_graph::kMaxLanes; ++lane)
         for (int t = 0; t < g->n_types; ++t)
             if (g->types[t].lane == lane) epilogue(t, 1);
     for (int gi : order) {
@@ -944,7 +950,7 @@ void run_forward(dgn_graph *g, float rate, StepDeps &D) {
         }
         produced(g, D.S2[gi], G.lane);
     }
-    for (int lane = 0; lane < 2; ++lane)
+    for (int lane = 0; lane < dgn_graph::kMaxLanes; ++lane)
         for (int t = 0; t < g->n_types; ++t)
             if (g->types[t].lane == lane) epilogue(t, 2);
 }
@@ -1051,7 +1057,7 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam) {
         }
         produced(g, D.dH[gi], G.lane);
     }
-    for (int lane = 0; lane < 2; ++lane)
+    for (int lane = 0; lane < dgn_graph::kMaxLanes; ++lane)
         for (int t = 0; t < g->n_types; ++t) {
             NodeType &T = g->types[t];
             if (T.lane != lane) continue;
@@ -1429,7 +1435,7 @@ extern "C" int dgn_graph_create(dgn_graph **out, int device, int n_types, const 
         int lo = 0, hi = 0;
         CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CUDA_CHECK(cudaStreamCreateWithPriority(&g->stream, cudaStreamNonBlocking, hi));
-        CUDA_CHECK(cudaStreamCreateWithPriority(&g->stream2, cudaStreamNonBlocking, lo));
+        for (int l = 1; l < dgn_graph::kMaxLanes; ++l) CUDA_CHECK(cudaStreamCreateWithPriority(&g->side[l], cudaStreamNonBlocking, lo));
         CUDA_CHECK(cudaStreamCreateWithPriority(&g->stream3, cudaStreamNonBlocking, lo));
         CUDA_CHECK(cudaEventCreateWithFlags(&g->mask_go, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&g->mask_done, cudaEventDisableTiming));
@@ -1513,7 +1519,8 @@ extern "C" int dgn_graph_destroy(dgn_graph *g) {
     }
     for (auto &e : g->dep_events) cudaEventDestroy(e);
     if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
-    if (g->stream2) cudaStreamDestroy(g->stream2);
+    for (int l = 1; l < dgn_graph::kMaxLanes; ++l)
+        if (g->side[l]) cudaStreamDestroy(g->side[l]);
     if (g->stream3) cudaStreamDestroy(g->stream3);
     if (g->mask_go) cudaEventDestroy(g->mask_go);
     if (g->mask_done) cudaEventDestroy(g->mask_done);
@@ -1641,12 +1648,25 @@ extern "C" int dgn_graph_finalize(dgn_graph *g) {
     // rest on lane 1 so that their short kernels fill the gaps; per-type kernels follow their row groups
     bool any_staged = false;
     for (auto &G : g->groups) any_staged = any_staged || G.staged;
-    for (auto &G : g->groups) G.lane = (g->two_lanes && any_staged && !G.staged) ? 1 : 0;
+    // the side groups get one lane each (round robin when there are more groups than lanes; DGN_SIDE_LANES=1 puts them
+    // all on one lane, the round-1 schedule)
+    int side_lanes = dgn_graph::kMaxLanes - 1;
+    if (const char *e = getenv("DGN_SIDE_LANES")) side_lanes = std::max(1, std::min(side_lanes, atoi(e)));
+    int next = 0;
+    g->n_lanes = 1;
+    for (auto &G : g->groups) {
+        G.lane = 0;
+        if (g->two_lanes && any_staged && !G.staged) {
+            G.lane = 1 + next++ % side_lanes;
+            g->n_lanes = std::max(g->n_lanes, G.lane + 1);
+        }
+    }
     for (auto &T : g->types) {
-        T.lane = 1;
+        T.lane = -1;
         for (int gi : T.row_groups)
             if (g->groups[gi].lane == 0) T.lane = 0;
-        if (!g->two_lanes || !any_staged) T.lane = 0;
+        if (T.lane < 0 && !T.row_groups.empty()) T.lane = g->groups[T.row_groups[0]].lane;
+        if (T.lane < 0 || !g->two_lanes || !any_staged) T.lane = 0;
     }
     g->finalized = true;
     DGN_API_END
