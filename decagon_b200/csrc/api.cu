@@ -351,6 +351,7 @@ struct Group {
     // work buffers
     float *part1 = nullptr, *part2 = nullptr, *Y1 = nullptr, *n1 = nullptr, *Y2 = nullptr, *n2 = nullptr;
     float *P2 = nullptr, *dS = nullptr, *G2 = nullptr, *bwd_partial = nullptr, *dW2part = nullptr, *dHpart = nullptr;
+    float *rows1 = nullptr, *rows2 = nullptr;  // partitioned gather-path group: this rank's row sums [P][n_i][32] (what it publishes)
     uint32_t *mask1 = nullptr, *mask2 = nullptr;
     long long mask1_words = 0, mask2_words = 0;
     bool dense_tc = false;  // layer-2 contractions on tcgen05 (dense_tc.cu)
@@ -537,7 +538,7 @@ void free_group_device(Group &G) {
     dev_free(G.wstart_bwd);
     G.slots1 = SlotTable(), G.slots2 = SlotTable(), G.slots_bwd = SlotTable();
     dev_free(G.rel_ids);
-    float **bufs[] = {&G.part1, &G.part2, &G.Y1, &G.n1, &G.Y2, &G.n2, &G.P2, &G.dS, &G.G2, &G.bwd_partial, &G.dW2part, &G.dHpart, &G.P1buf, &G.G1buf};
+    float **bufs[] = {&G.rows1, &G.rows2, &G.part1, &G.part2, &G.Y1, &G.n1, &G.Y2, &G.n2, &G.P2, &G.dS, &G.G2, &G.bwd_partial, &G.dW2part, &G.dHpart, &G.P1buf, &G.G1buf};
     for (float **b : bufs) dev_free(*b);
     dev_free(G.mask1);
     dev_free(G.mask2);
@@ -645,6 +646,10 @@ void build_group(dgn_graph *g, Group &G) {
     } else {
         G.part1 = dev_alloc<float>(panel_floats(P1, G.fwd_seg.n_seg));
         G.part2 = dev_alloc<float>(panel_floats(1, G.fwd_seg.n_seg));
+        if (G.partitioned) {
+            G.rows1 = dev_alloc<float>(panel_floats(P1, n_i));
+            G.rows2 = dev_alloc<float>(panel_floats(1, n_i));
+        }
     }
     G.Y1 = dev_alloc<float>(panel_floats(P1, n_i));
     G.n1 = dev_alloc<float>(n_i);
@@ -783,9 +788,9 @@ void run_forward(dgn_graph *g, float rate, StepDeps &D) {
         if (g->two_lanes) {
             CUDA_CHECK(cudaEventRecord(g->mask_go, g->stream));  // after the join: last step's readers of mask2 are done
             CUDA_CHECK(cudaStreamWaitEvent(g->stream3, g->mask_go, 0));
-            for (int lane = 1; lane >= 0; --lane)  // small ones first
+            for (int side = 1; side >= 0; --side)  // the side groups' (small) masks first
                 for (auto &G : g->groups) {
-                    if (G.lane != lane) continue;
+                    if ((G.lane != 0) != (side == 1)) continue;
                     launch_gen_mask(G.mask2, G.mask2_words, (long long)G.n_j * g->d1, G.n_j * P1, G.rel_ids, kStreamDropout2, g->dyn_dev,
                                     g->stream3);
                     g->launches++;
@@ -854,7 +859,21 @@ void run_forward(dgn_graph *g, float rate, StepDeps &D) {
             a.op = op, a.op_rows = (int)op_rows;
             a.partial = part, a.force_partial = 1;
             a.mask = mask, a.col_mask = mask != nullptr, a.scale = scale;
-            launch_spmm(a, P, s);
+            if (G.partitioned) {
+                // this rank's row sums are what it publishes: rows of one segment are written directly, hub rows are
+                // reduced in order, rows without a non-zero stay zero
+                float *rows = part == G.part1 ? G.rows1 : G.rows2;
+                CUDA_CHECK(cudaMemsetAsync(rows, 0, panel_floats(P, G.n_i) * sizeof(float), s));
+                a.out = rows, a.out_rows = G.n_i, a.force_partial = 0;
+                launch_spmm(a, P, s);
+                if (G.fwd_seg.n_multi > 0) {
+                    a.mask = nullptr, a.col_mask = 0;
+                    launch_seg_reduce(a, G.fwd_seg.multi_rows, G.fwd_seg.n_multi, P, s);
+                    g->launches++;
+                }
+            } else {
+                launch_spmm(a, P, s);
+            }
         }
         g->launches++;
     };
@@ -921,7 +940,8 @@ void run_forward(dgn_graph *g, float rate, StepDeps &D) {
             } else {
                 spmm_fwd(G, g->params + G.w1_off, P1, (long long)G.Kl * G.F_j, G.part1, G.slots1, G.wstart1, drop ? G.mask1 : nullptr);
             }
-            if (G.partitioned) exchange(g, G, 0, G.part1, G.slots1.n_slots, lane_stream(g, G.lane));
+            if (G.partitioned && G.staged) exchange(g, G, 0, G.part1, G.slots1.n_slots, lane_stream(g, G.lane));
+            else if (G.partitioned) exchange(g, G, 0, G.rows1, 1, lane_stream(g, G.lane));
         }
         produced(g, D.S1[gi], G.lane);
     }
@@ -946,7 +966,8 @@ void run_forward(dgn_graph *g, float rate, StepDeps &D) {
         {
             PhaseScope ph(g, "spmm_fwd2", gi, G.lane);
             spmm_fwd(G, G.P2, 1, (long long)G.Kl * G.n_j, G.part2, G.slots2, G.wstart2, nullptr);
-            if (G.partitioned) exchange(g, G, 1, G.part2, G.slots2.n_slots, lane_stream(g, G.lane));
+            if (G.partitioned && G.staged) exchange(g, G, 1, G.part2, G.slots2.n_slots, lane_stream(g, G.lane));
+            else if (G.partitioned) exchange(g, G, 1, G.rows2, 1, lane_stream(g, G.lane));
         }
         produced(g, D.S2[gi], G.lane);
     }
@@ -1614,7 +1635,8 @@ extern "C" int dgn_graph_finalize(dgn_graph *g) {
     }
     for (auto &G : g->groups) {
         // multi-GPU: groups that take the staged path (many small relations) are partitioned by relation
-        G.partitioned = g->world > 1 && g->allow_staged && staged_supported(G.n_i, G.n_j, G.K) && G.K >= 8 * g->world;
+        // (also those whose operand tiles exceed shared memory and take the gather path: config #5)
+        G.partitioned = g->world > 1 && G.K >= 8 * g->world;
         std::vector<int> loc;
         if (G.partitioned) {
             std::vector<int64_t> w(G.K);

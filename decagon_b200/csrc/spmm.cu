@@ -333,6 +333,10 @@ __device__ __forceinline__ int task_count(int h, int s) {
 }
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// one instruction moves a whole contiguous range towards L2 (bytes: a multiple of 16)
+__device__ __forceinline__ void bulk_prefetch_l2(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 
 constexpr int kRingStages = 4;
 constexpr int kRingBlockPs = 8;                                  // pair-steps per block
@@ -533,24 +537,25 @@ __global__ void __launch_bounds__(kStagedThreads, 1) spmm_tstaged_kernel(const T
     float alpha = 0.f, omb1 = 0.f, omb2 = 0.f, eps = 0.f;
     if (a.adam_p != nullptr) alpha = a.dyn->alpha, omb1 = a.dyn->omb1, omb2 = a.dyn->omb2, eps = a.dyn->eps;
 
+    // The optimizer state (p, m, v) of a relation's rows is one contiguous block per panel: it is moved towards L2 a
+    // whole relation ahead with bulk prefetches, so that the loads that follow each row's gather do not wait for HBM
+    auto prefetch_state = [&](int t) {
+        if (a.adam_p == nullptr || t >= n_rel || threadIdx.x >= 3 * P) return;
+        const int k = a.slot_rel[r_begin + t];
+        const int pp = threadIdx.x / 3, which = threadIdx.x % 3;
+        const float *base = which == 0 ? a.adam_p : which == 1 ? a.adam_m : a.adam_v;
+        bulk_prefetch_l2(base + ((size_t)pp * out_rows + (size_t)k * a.n_out_rows) * 32, (uint32_t)a.n_out_rows * 128u);
+    };
+    prefetch_state(0);
     for (int t = 0; t < n_rel; ++t) {
         const int k = a.slot_rel[r_begin + t];
         const int h = h_next;
+        prefetch_state(t + 1);
         const int *__restrict__ orow = a.orow + (size_t)k * a.orow_stride + warp * a.rpq * 4 + quarter;
         if (t + 1 < n_rel) h_next = __ldg(a.hdr + ((size_t)a.slot_rel[r_begin + t + 1] * kTsWarps + warp) * 4 + (lane & 3));
         for (int s = 0; s < a.rpq; ++s) {
             const int n2 = task_count(h, s);
             const int c = __ldg(orow + s * 4);
-            if (a.adam_p != nullptr && c >= 0) {
-                // the optimizer state of this row is needed right after the gather: start moving it to L2
-#pragma unroll
-                for (int pp = 0; pp < P; ++pp) {
-                    const size_t o = ((size_t)pp * out_rows + (size_t)k * a.n_out_rows + c) * 32 + (l8 << 2);
-                    prefetch_l2(a.adam_p + o);
-                    prefetch_l2(a.adam_m + o);
-                    prefetch_l2(a.adam_v + o);
-                }
-            }
             float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
             stream_steps(rd, n2, [&](int off, int vbits) {
                 gather_fma(s0, xrow, off, vbits);

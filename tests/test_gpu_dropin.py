@@ -456,8 +456,11 @@ def test_learning_curve_matches_the_reference_run():
             itr += 1
             if int(idx) == 0:
                 type0.append((itr, float(cost)))
-    first = np.mean([c for i, c in type0 if i <= 24])
+    # the file's first row is the edge-type-0 minibatch at iteration 24; ours are at 4 j + 1: average the three
+    # nearest ones (one minibatch loss of 512 edges scatters by a few units)
+    first = np.mean([c for i, c in type0 if 16 < i <= 28])
     last = np.mean([c for i, c in type0 if i > 1200 - 48])
+    print('edge-type-0 losses:', [(i, round(c, 2)) for i, c in type0[:10]], '...', [(i, round(c, 2)) for i, c in type0[-6:]])
     # validation AUROC of (0,0,0) as DecagonAccuracyEvaluator computes it (sigmoid of predictions at the edges),
     # positives = val_edges, negatives = as many uniformly drawn non-edges (the fork that wrote the file drew 110)
     rel = (0, 0, 0)

@@ -24,11 +24,15 @@ def _free_port():
     return port
 
 
-def test_two_ranks_match_one_gpu():
+@pytest.mark.parametrize('env', [{}, {'DGN_DISABLE_STAGED': '1'}, {'DGN_CUDA_GRAPH': '0'}])
+def test_two_ranks_match_one_gpu(env):
+    """env = {}: the staged (shared-memory) kernels with the step replayed as a CUDA graph; DGN_DISABLE_STAGED: the
+    relation partition of a group on the gather path (what config #5's 6 450-drug group takes); DGN_CUDA_GRAPH=0:
+    every kernel issued from the host."""
     if _lib.device_count() < 2:
         pytest.skip('needs two GPUs (gpurun --gpus 2)')
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
            '--master-port', str(_free_port()), os.path.join(ROOT, 'tests', 'multigpu_check.py')]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, **env))
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert 'multigpu_check OK' in out.stdout
