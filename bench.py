@@ -33,12 +33,13 @@ def log(*a):
 
 
 # ----------------------------------------------------------------------------- workload
-def build_workload(config, scale):
+def build_workload(config, scale, decoder=None):
     from decagon_b200 import datasets
     from decagon_b200.deep.minibatch import EdgeMinibatchIterator
     t0 = time.time()
     if config == 'toy':
-        inputs = datasets.toy_graph()
+        # config #1 (main.py's decoders) or config #2: every group on the same decoder kind
+        inputs = datasets.toy_graph({g: decoder for g in datasets.DEFAULT_DECODERS} if decoder else None)
     else:
         inputs = datasets.polypharmacy_graph(scale=scale)
     np.random.seed(0)
@@ -184,7 +185,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    inputs, it = build_workload(args.config, args.scale)
+    inputs, it = build_workload(args.config, args.scale, args.decoder)
     params = glorot_params(inputs, HYPER['hidden1'], HYPER['hidden2'])
     n_warm = max(args.warmup, 1)
     sec, n_timed, sample = cpu_port_steps(inputs, it, params, args.steps, n_warm, args.reference_budget)
@@ -204,7 +205,8 @@ def run_reference(args):
 
 
 def workload_config(args, inputs):
-    return {'workload': 'polypharmacy-shape synthetic (BASELINE config #3)' if args.config == 'poly' else 'toy (config #1)',
+    toy = 'toy (config #1)' if not args.decoder else 'toy, every group %s (config #2)' % args.decoder
+    return {'workload': ('polypharmacy-shape synthetic (BASELINE config #%d)' % (3 if args.scale == 1 else 5)) if args.config == 'poly' else toy,
             'n_proteins': inputs.n_nodes[0], 'n_drugs': inputs.n_nodes[1],
             'relation_matrices': sum(inputs.edge_types.values()), 'hidden': [HYPER['hidden1'], HYPER['hidden2']],
             'batch': HYPER['batch_size'], 'dropout': HYPER['dropout'], 'loss': 'hinge', 'optimizer': 'adam(tf1)',
@@ -284,7 +286,7 @@ def run_ours(args):
         # path is the library's own peer-memory exchange over NVLink, not a torch.distributed collective
         dist.init_process_group('gloo')
 
-    inputs, it = build_workload(args.config, args.scale)
+    inputs, it = build_workload(args.config, args.scale, args.decoder)
     t0 = time.time()
     # the reference's own construction sequence: placeholders, model, optimizer, session
     placeholders, model, opt = build_trainable(inputs, it)
@@ -508,6 +510,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='poly', choices=['poly', 'toy'])
     ap.add_argument('--scale', type=int, default=1)
+    ap.add_argument('--decoder', default=None, choices=['innerproduct', 'distmult', 'bilinear', 'dedicom'],
+                    help='toy config only: put every group on this decoder (BASELINE config #2)')
     ap.add_argument('--reference-budget', type=float, default=150.0, help='seconds of timed CPU steps')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-equivalence', action='store_true', help='skip the N-GPU vs 1-GPU equivalence steps (N > 1)')

@@ -48,7 +48,6 @@ __device__ unsigned long long g_tc_prof[8];
 #define TC_CLK(i) do { } while (0)
 #endif
 constexpr int kTile = 128;  // rows per tile = threads
-constexpr int kDw2Threads = 256;  // dw2: two threads per tile row write the operand tiles (8 warps per CTA hide their latency)
 
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
@@ -428,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, 2) dh_tc_kernel(const DenseArgs a) {
 // Loads are coalesced and one row tile ahead (issued right after the tiles of the current one are written); the
 // read-back of a finished unit happens after the wait that precedes the next tile's writes.
 template <int D1>
-__global__ void __launch_bounds__(kDw2Threads, 2) dw2_tc_kernel(const DenseArgs a, int n_tiles) {
+__global__ void __launch_bounds__(kThreads, 2) dw2_tc_kernel(const DenseArgs a, int n_tiles) {
     constexpr int KB = D1 / 32;
     constexpr uint32_t kIdesc = idesc_tf32(128, 64, 1, 1);
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -442,20 +441,19 @@ __global__ void __launch_bounds__(kDw2Threads, 2) dw2_tc_kernel(const DenseArgs 
     const int n_units = a.K * n_chunks;
     const int u_begin = (int)((long long)blockIdx.x * n_units / gridDim.x), u_end = (int)((long long)(blockIdx.x + 1) * n_units / gridDim.x);
     if (D1 < 64) {  // the atoms of panel 1 are never written: they must read as zero
-        for (int i = tid; i < 65536 / 16; i += kDw2Threads) st128(As + 16 * i, zero4());
+        for (int i = tid; i < 65536 / 16; i += kThreads) st128(As + 16 * i, zero4());
     }
     const uint32_t tmem = tc_prologue<64>(&tmem_slot, &mma_done, smem);
-    const int lrow = tid >> 3, lc = tid & 7;      // loads: rows lrow + 32 i of the tile, 16-byte chunk lc
-    const uint32_t toff = mn_off(lrow, lc);       // (lrow + 32 i) & 7 == lrow & 7
+    const int lrow = tid >> 3, lc = tid & 7;      // loads: rows lrow + 16 i of the tile, 16-byte chunk lc
+    const uint32_t toff = mn_off(lrow, lc);       // (lrow + 16 i) & 7 == lrow & 7
     const float sc = a.mask != nullptr ? a.scale : 1.f;
 
-    constexpr int RPT = kTile * 8 / kDw2Threads;  // rows per thread
-    uint32_t mk[KB][RPT];
-    float4 h[KB][RPT], gv[RPT];
+    uint32_t mk[KB][8];
+    float4 h[KB][8], gv[8];
     auto fetch = [&](int k, int t) {
 #pragma unroll
-        for (int i = 0; i < RPT; ++i) {
-            const int r = t * kTile + lrow + (kDw2Threads / 8) * i;
+        for (int i = 0; i < 8; ++i) {
+            const int r = t * kTile + lrow + 16 * i;
             const bool ok = r < a.n_j;
 #pragma unroll
             for (int p = 0; p < KB; ++p) {
@@ -468,16 +466,14 @@ __global__ void __launch_bounds__(kDw2Threads, 2) dw2_tc_kernel(const DenseArgs 
     // read the finished unit back: rows m (hi) + rows 64 + m (lo), columns n (hi) + 32 + n (lo)
     auto unit_epilogue = [&](int k, int chunk) {
         float v0[32], v1[32];
-        if (warp < 4) {  // the four warps that own the 128 TMEM lanes
-            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-            tmem_ld32(taddr, v0);
-            tmem_ld32(taddr + 32, v1);
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+        tmem_ld32(taddr, v0);
+        tmem_ld32(taddr + 32, v1);
 #pragma unroll
-            for (int n = 0; n < 32; ++n) v0[n] += v1[n];
-            if (warp >= 2) {
+        for (int n = 0; n < 32; ++n) v0[n] += v1[n];
+        if (warp >= 2) {
 #pragma unroll
-                for (int n = 0; n < 32; ++n) stage[(tid - 64) * 33 + n] = v0[n];
-            }
+            for (int n = 0; n < 32; ++n) stage[(tid - 64) * 33 + n] = v0[n];
         }
         fence_before();
         __syncthreads();
@@ -523,8 +519,8 @@ __global__ void __launch_bounds__(kDw2Threads, 2) dw2_tc_kernel(const DenseArgs 
         }
         TC_CLK(0);
 #pragma unroll
-        for (int i = 0; i < RPT; ++i) {
-            const int kblk = (kDw2Threads / 64) * i + (lrow >> 3);  // (lrow + (kDw2Threads / 8) i) >> 3
+        for (int i = 0; i < 8; ++i) {
+            const int kblk = 2 * i + (lrow >> 3);  // (lrow + 16 i) >> 3
 #pragma unroll
             for (int p = 0; p < KB; ++p) {
                 float4 v, hi, lo;
@@ -658,7 +654,7 @@ void launch_dw2_tc(const DenseArgs &a, int D1, cudaStream_t s) {
     const int grid = std::max(1, std::min(a.K * a.n_rb, a.n_slots));
     if (D1 == 64) {
         set_smem(dw2_tc_kernel<64>, bytes);
-        dw2_tc_kernel<64><<<grid, kDw2Threads, bytes, s>>>(a, n_tiles);
+        dw2_tc_kernel<64><<<grid, kThreads, bytes, s>>>(a, n_tiles);
 #ifdef DGN_TC_PROFILE
         if (a.K > 100) {
             unsigned long long h[8];
@@ -673,7 +669,7 @@ void launch_dw2_tc(const DenseArgs &a, int D1, cudaStream_t s) {
 #endif
     } else {
         set_smem(dw2_tc_kernel<32>, bytes);
-        dw2_tc_kernel<32><<<grid, kDw2Threads, bytes, s>>>(a, n_tiles);
+        dw2_tc_kernel<32><<<grid, kThreads, bytes, s>>>(a, n_tiles);
     }
     CUDA_CHECK(cudaGetLastError());
 }
