@@ -263,11 +263,14 @@ def model_params(model):
 
 
 def equivalence_steps(eng, batches, n_types):
-    """Three training steps from the initial parameters, then one forward: (losses, embeddings)."""
+    """One forward from the initial parameters, three training steps, one more forward:
+    (losses, embeddings after the steps, embeddings before them)."""
+    eng.forward(HYPER['dropout'], SEED, 99)
+    Z0 = [eng.embeddings(t) for t in range(n_types)]
     losses = [float(eng.train_step(r, b, loss='hinge', margin=HYPER['margin'], lr=HYPER['lr'], dropout=HYPER['dropout'],
                                    seed=SEED, step=i)) for i, (r, b) in enumerate(batches)]
     eng.forward(0.0, SEED, 0)
-    return losses, [eng.embeddings(t) for t in range(n_types)]
+    return losses, [eng.embeddings(t) for t in range(n_types)], Z0
 
 
 def run_ours(args):
@@ -325,7 +328,7 @@ def run_ours(args):
 
     if world > 1 and not args.no_equivalence:
         import hashlib
-        losses_p, Z_p = equivalence_steps(eng, eq_batches, n_types)
+        losses_p, Z_p, Z0_p = equivalence_steps(eng, eq_batches, n_types)
         digests = [None] * world
         dist.all_gather_object(digests, hashlib.sha256(b''.join(z.tobytes() for z in Z_p)).hexdigest())
         if rank == 0:
@@ -333,9 +336,13 @@ def run_ours(args):
             equivalence = {
                 'what': '3 training steps + 1 forward from identical parameters: %d-rank partitioned engine vs the '
                         'un-partitioned engine on rank 0' % world,
+                'embeddings_first_forward_rel_err': max(rel(a, b) for a, b in zip(Z0_p, ref_eq[2])),
                 'loss_first_step_rel_err': abs(losses_p[0] - ref_eq[0][0]) / abs(ref_eq[0][0]),
                 'loss_rel_err_max': max(abs(a - b) / abs(b) for a, b in zip(losses_p, ref_eq[0])),
-                'embeddings_rel_err_max': max(rel(a, b) for a, b in zip(Z_p, ref_eq[1])),
+                'embeddings_after_3_adam_steps_rel_err': max(rel(a, b) for a, b in zip(Z_p, ref_eq[1])),
+                'note': 'same parameters (first forward, first loss): the float32 contract 1e-5; after Adam steps the '
+                        'trajectories separate because the first updates move every weight by ~lr * sign(g), also where '
+                        'g is zero up to re-association',
                 'ranks_bit_identical': all(d == digests[0] for d in digests),
                 'tolerance': 1e-5, 'losses': losses_p, 'losses_one_gpu': ref_eq[0]}
         sess.run(tf.global_variables_initializer())  # back to the initial parameters and zeroed Adam slots

@@ -403,6 +403,7 @@ struct dgn_graph {
     int *exchange_error_host = nullptr;
     bool two_lanes = true;
     bool fuse_adam = true;  // Adam of the layer-1 weights inside the kernel that produces their gradient
+    bool gather_row_sums = true;  // gather path: segments reduced to row sums before the epilogue (DGN_GATHER_ROWSUMS=0: in it)
     bool keep_grads = false;  // dgn_keep_gradients: every gradient is materialised (no fused Adam)
     std::vector<cudaEvent_t> dep_events;  // pool, reused every step
     size_t dep_next = 0;
@@ -646,10 +647,8 @@ void build_group(dgn_graph *g, Group &G) {
     } else {
         G.part1 = dev_alloc<float>(panel_floats(P1, G.fwd_seg.n_seg));
         G.part2 = dev_alloc<float>(panel_floats(1, G.fwd_seg.n_seg));
-        if (G.partitioned) {
-            G.rows1 = dev_alloc<float>(panel_floats(P1, n_i));
-            G.rows2 = dev_alloc<float>(panel_floats(1, n_i));
-        }
+        G.rows1 = dev_alloc<float>(panel_floats(P1, n_i));
+        G.rows2 = dev_alloc<float>(panel_floats(1, n_i));
     }
     G.Y1 = dev_alloc<float>(panel_floats(P1, n_i));
     G.n1 = dev_alloc<float>(n_i);
@@ -859,9 +858,10 @@ void run_forward(dgn_graph *g, float rate, StepDeps &D) {
             a.op = op, a.op_rows = (int)op_rows;
             a.partial = part, a.force_partial = 1;
             a.mask = mask, a.col_mask = mask != nullptr, a.scale = scale;
-            if (G.partitioned) {
-                // this rank's row sums are what it publishes: rows of one segment are written directly, hub rows are
-                // reduced in order, rows without a non-zero stay zero
+            if (g->gather_row_sums || G.partitioned) {
+                // row sums [P][n_i][32] (what a partitioned group publishes, and what the epilogue reads with one load
+                // per row instead of a walk over the row's segments): rows of one segment are written directly, hub
+                // rows are reduced in order by a warp each, rows without a non-zero stay zero
                 float *rows = part == G.part1 ? G.rows1 : G.rows2;
                 CUDA_CHECK(cudaMemsetAsync(rows, 0, panel_floats(P, G.n_i) * sizeof(float), s));
                 a.out = rows, a.out_rows = G.n_i, a.force_partial = 0;
@@ -891,6 +891,11 @@ void run_forward(dgn_graph *g, float rate, StepDeps &D) {
             eg.partial = layer == 1 ? G.part1 : G.part2;
             eg.row_seg_ptr = G.staged ? nullptr : G.fwd_seg.row_seg_ptr;
             eg.n_slots = layer == 1 ? G.slots1.n_slots : G.slots2.n_slots;
+            if (!G.staged && g->gather_row_sums) {
+                eg.partial = layer == 1 ? G.rows1 : G.rows2;
+                eg.row_seg_ptr = nullptr;
+                eg.n_slots = 1;
+            }
             if (G.partitioned) {
                 eg.n_peers = g->world;
                 for (int r = 0; r < g->world; ++r) eg.peer[r] = peer_ptr(g, G, layer - 1, r);
@@ -1490,6 +1495,8 @@ extern "C" int dgn_graph_create(dgn_graph **out, int device, int n_types, const 
     g->fuse_adam = !(env && env[0] == '0');
     env = getenv("DGN_SINGLE_STREAM");
     g->two_lanes = !(env && env[0] == '1');
+    env = getenv("DGN_GATHER_ROWSUMS");
+    g->gather_row_sums = !(env && env[0] == '0');
     env = getenv("DGN_CUDA_GRAPH");
     g->use_graphs = !(env && env[0] == '0');
     env = getenv("DGN_DISABLE_TSTAGED");
