@@ -403,7 +403,8 @@ struct dgn_graph {
     int *exchange_error_host = nullptr;
     bool two_lanes = true;
     bool fuse_adam = true;  // Adam of the layer-1 weights inside the kernel that produces their gradient
-    bool gather_row_sums = true;  // gather path: segments reduced to row sums before the epilogue (DGN_GATHER_ROWSUMS=0: in it)
+    bool gather_row_sums = false;  // gather path: segments reduced to row sums BEFORE the epilogue instead of inside it
+                                   // (DGN_GATHER_ROWSUMS=1; measured 1.764 vs 1.720 ms per step on one GPU: two more launches per group)
     bool keep_grads = false;  // dgn_keep_gradients: every gradient is materialised (no fused Adam)
     std::vector<cudaEvent_t> dep_events;  // pool, reused every step
     size_t dep_next = 0;
@@ -1496,7 +1497,7 @@ extern "C" int dgn_graph_create(dgn_graph **out, int device, int n_types, const 
     env = getenv("DGN_SINGLE_STREAM");
     g->two_lanes = !(env && env[0] == '1');
     env = getenv("DGN_GATHER_ROWSUMS");
-    g->gather_row_sums = !(env && env[0] == '0');
+    g->gather_row_sums = env && env[0] == '1';
     env = getenv("DGN_CUDA_GRAPH");
     g->use_graphs = !(env && env[0] == '0');
     env = getenv("DGN_DISABLE_TSTAGED");
