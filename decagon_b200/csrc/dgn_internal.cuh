@@ -35,6 +35,20 @@ struct Failure {
                      cudaGetErrorString(err__));                                                    \
     } while (0)
 
+// cudaFuncSetAttribute is per device: launchers remember which devices they have configured, not "done once"
+// (one process may own several graph handles on different GPUs)
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool first() {  // true the first time it is called on the current device
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64) return true;
+        const bool f = !done[dev];
+        done[dev] = true;
+        return f;
+    }
+};
+
 // ---------------------------------------------------------------- host-side sparse structures
 struct HostCsr {
     int n_rows = 0, n_cols = 0;

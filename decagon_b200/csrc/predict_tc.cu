@@ -200,10 +200,9 @@ void launch_predict_tc(const PredictArgs &a, int n_sm, cudaStream_t s) {
     const int n_nt = (a.n_j + kMaxN - 1) / kMaxN;
     const int NT = std::max(16, (((a.n_j + n_nt - 1) / n_nt) + 15) / 16 * 16);  // even split, MMA N granularity 16
     const int n_workers = std::max(1, std::min(a.count, 2 * n_sm / n_nt));
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.first()) {
         CUDA_CHECK(cudaFuncSetAttribute(predict_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        configured = true;
     }
     predict_tc_kernel<<<n_nt * n_workers, kThreads, kSmemBytes, s>>>(a, n_workers, NT);
     CUDA_CHECK(cudaGetLastError());

@@ -638,11 +638,10 @@ bool staged_supported(int n_i, int n_j, int K) {
 template <int RPQ>
 static void launch_staged_t(const StagedArgs &a, cudaStream_t s) {
     const size_t smem = staged_smem_bytes(a.n_j);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.first()) {
         CUDA_CHECK(cudaFuncSetAttribute(spmm_staged_kernel<RPQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         200 * 1024));
-        configured = true;
     }
     spmm_staged_kernel<RPQ><<<a.n_slots * a.P, kStagedThreads, smem, s>>>(a);
     CUDA_CHECK(cudaGetLastError());
@@ -669,10 +668,9 @@ bool tstaged_supported(int n_i, int n_j, int K, int P) {
 
 template <int RPQ>
 static void launch_staged3_t(const TaskArgs &a, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.first()) {
         CUDA_CHECK(cudaFuncSetAttribute(spmm_staged3_kernel<RPQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
-        configured = true;
     }
     spmm_staged3_kernel<RPQ><<<a.n_slots * a.P, kStagedThreads, staged3_smem(a.n_op_rows), s>>>(a);
     CUDA_CHECK(cudaGetLastError());
@@ -688,10 +686,9 @@ void launch_spmm_staged3(const TaskArgs &a, cudaStream_t s) {
 
 template <int P>
 static void launch_tstaged_t(const TaskArgs &a, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.first()) {
         CUDA_CHECK(cudaFuncSetAttribute(spmm_tstaged_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
-        configured = true;
     }
     spmm_tstaged_kernel<P><<<a.n_slots, kStagedThreads, tstaged_smem(a.n_op_rows, P), s>>>(a);
     CUDA_CHECK(cudaGetLastError());
