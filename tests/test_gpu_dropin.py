@@ -527,3 +527,51 @@ def test_remasked_relations_rebuild_only_their_group():
     assert all(np.array_equal(a[n][g], b[n][g]) for n in a for g in a[n])
     eng.close()
     ref.close()
+
+
+def test_toy_graph_reaches_the_upstream_test_metrics():
+    """Second reference-held end-to-end artefact: ``theirBadResults.txt``, the final test metrics of the upstream
+    script on the toy graph of ``main.py:134-183`` (config #1: 500 genes, 400 drugs, 10 relation matrices, 50 epochs,
+    bilinear x 3 + dedicom, hidden 64 / 32, batch 512, dropout 0.1, lr 1e-3, margin 0.1): per-relation test AUROC
+    0.741 - 0.834 (mean 0.787).  Same script through the drop-in classes (``main.py:246-275``: shuffle, while not end:
+    one optimizer step), then AUROC of every relation's held-out edges (validation + test split) against as many
+    uniformly drawn non-edges: every relation >= 0.65 and the mean within 0.72 - 0.90."""
+    from sklearn import metrics
+    from decagon_b200.evaluator import sigmoid
+    inputs = datasets.toy_graph()
+    placeholders, minibatch, model, opt = build_trainable(inputs, batch_size=512)
+    sess = tf.Session(seed=SEED)
+    sess.run(tf.global_variables_initializer())
+    np.random.seed(0)
+    steps = 0
+    for epoch in range(50):
+        minibatch.shuffle()
+        while not minibatch.end():
+            fd = minibatch.update_feed_dict(minibatch.next_minibatch_feed_dict(placeholders), 0.1, placeholders)
+            sess.run([opt.opt_op, opt.cost, opt.batch_edge_type_idx], feed_dict=fd)
+            steps += 1
+    rng = np.random.RandomState(2)
+    aurocs = {}
+    for et in inputs.edge_types:
+        for k in range(inputs.edge_types[et]):
+            fd[placeholders['dropout']] = 0
+            fd[placeholders['batch_edge_type_idx']] = minibatch.edge_type2idx[et[0], et[1], k]
+            fd[placeholders['batch_row_edge_type']], fd[placeholders['batch_col_edge_type']] = et
+            pred = sigmoid(sess.run(opt.predictions, feed_dict=fd))
+            pos = np.vstack([np.asarray(minibatch.val_edges[et][k]).reshape(-1, 2),
+                             np.asarray(minibatch.test_edges[et][k]).reshape(-1, 2)]).astype(np.int64)
+            dense = inputs.adj_mats[et][k].toarray()
+            neg = []
+            while len(neg) < len(pos):
+                u, v = rng.randint(0, dense.shape[0]), rng.randint(0, dense.shape[1])
+                if dense[u, v] == 0:
+                    neg.append((u, v))
+            neg = np.asarray(neg)
+            scores = np.concatenate([pred[pos[:, 0], pos[:, 1]], pred[neg[:, 0], neg[:, 1]]])
+            labels = np.concatenate([np.ones(len(pos)), np.zeros(len(neg))])
+            aurocs[et[0], et[1], k] = metrics.roc_auc_score(labels, scores)
+    mean = float(np.mean(list(aurocs.values())))
+    print('toy graph, %d steps: held-out AUROC per relation %s, mean %.3f (upstream 0.741 - 0.834, mean 0.787)'
+          % (steps, {k: round(v, 3) for k, v in aurocs.items()}, mean))
+    assert min(aurocs.values()) >= 0.65, aurocs
+    assert 0.72 <= mean <= 0.90, mean
