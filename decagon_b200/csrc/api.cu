@@ -403,6 +403,7 @@ struct dgn_graph {
     int *exchange_error_host = nullptr;
     bool two_lanes = true;
     bool fuse_adam = true;  // Adam of the layer-1 weights inside the kernel that produces their gradient
+    bool gate_lane0 = true;  // the staged kernels of lane 0 wait for the side groups' kernels of the same layer (see run_forward)
     bool gather_row_sums = false;  // gather path: segments reduced to row sums BEFORE the epilogue instead of inside it
                                    // (DGN_GATHER_ROWSUMS=1; measured 1.764 vs 1.720 ms per step on one GPU: two more launches per group)
     bool keep_grads = false;  // dgn_keep_gradients: every gradient is materialised (no fused Adam)
@@ -923,8 +924,8 @@ void run_forward(dgn_graph *g, float rate, StepDeps &D) {
         for (int gi : lo)
             if (g->groups[gi].lane == 0) order.push_back(gi);
     }
-    auto gate = [&](Group &G, std::vector<Dep> &deps) {  // lane 0 waits for every lane-1 group's partial sums
-        if (G.lane != 0 || !G.staged) return;
+    auto gate = [&](Group &G, std::vector<Dep> &deps) {  // lane 0 waits for every side group's partial sums
+        if (G.lane != 0 || !G.staged || !g->gate_lane0) return;
         for (int q = 0; q < g->n_groups; ++q)
             if (g->groups[q].lane != 0) consume(g, deps[q], 0);
         wait_mask2(0);  // or the staged kernel would starve the mask generation as well
@@ -1678,6 +1679,11 @@ extern "C" int dgn_graph_finalize(dgn_graph *g) {
     // rest on lane 1 so that their short kernels fill the gaps; per-type kernels follow their row groups
     bool any_staged = false;
     for (auto &G : g->groups) any_staged = any_staged || G.staged;
+    // The gate (lane 0's persistent kernels wait for the side groups of the layer so that they do not starve them) pays
+    // on one GPU, where those kernels run for 160-280 us; with several ranks they are short and the gate only
+    // serialises the two lanes.  DGN_GATE overrides.
+    g->gate_lane0 = g->world == 1;
+    if (const char *e = getenv("DGN_GATE")) g->gate_lane0 = e[0] != '0';
     // With several ranks the side groups get one lane each (round robin when there are more groups than lanes): lane 0's
     // kernels shrink with the rank count and the side groups become the critical path, so their short kernels should
     // overlap each other.  On one GPU a single side lane measured 1 % faster (the persistent lane-0 kernels fill the
