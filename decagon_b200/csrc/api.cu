@@ -352,7 +352,8 @@ struct Group {
     float *part1 = nullptr, *part2 = nullptr, *Y1 = nullptr, *n1 = nullptr, *Y2 = nullptr, *n2 = nullptr;
     float *P2 = nullptr, *dS = nullptr, *G2 = nullptr, *bwd_partial = nullptr, *dW2part = nullptr, *dHpart = nullptr;
     float *rows1 = nullptr, *rows2 = nullptr;  // partitioned gather-path group: this rank's row sums [P][n_i][32] (what it publishes)
-    uint32_t *mask1 = nullptr, *mask2 = nullptr;
+    uint32_t *mask1 = nullptr, *mask2 = nullptr;  // mask2: the buffer of mask2buf this step reads
+    uint32_t *mask2buf[2] = {nullptr, nullptr};
     long long mask1_words = 0, mask2_words = 0;
     bool dense_tc = false;  // layer-2 contractions on tcgen05 (dense_tc.cu)
     bool gen_feat = false;  // column type has general sparse features: layer 1 runs on P1 = X W1_k / G1 = A_k^T dS1
@@ -387,7 +388,14 @@ struct dgn_graph {
     cudaStream_t side[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // side[0] unused
     int n_lanes = 2;
     cudaStream_t stream3 = nullptr;  // layer-2 keep words of every group (integer ALU work beside lane 1's gathers)
-    cudaEvent_t mask_go = nullptr, mask_done = nullptr;
+    cudaEvent_t mask_go = nullptr, mask_done = nullptr, ahead_go = nullptr, ahead_done = nullptr;
+    // Layer-2 keep words drawn AHEAD: the masks of step t + 1 (same seed and rate assumed) are generated into the other
+    // buffer while step t's backward finishes on the side lanes; a step whose (seed, step, rate) match finds them ready
+    bool mask_ahead = true;  // DGN_MASK_AHEAD=0 disables
+    int mask_cur = 0;
+    bool ahead_valid = false;
+    uint64_t ahead_seed = 0;
+    uint32_t ahead_step = 0, ahead_thr = 0;
     bool own_stream = false;
     int rank = 0, world = 1;
     bool arena_ready = false;
@@ -544,7 +552,9 @@ void free_group_device(Group &G) {
     float **bufs[] = {&G.rows1, &G.rows2, &G.part1, &G.part2, &G.Y1, &G.n1, &G.Y2, &G.n2, &G.P2, &G.dS, &G.G2, &G.bwd_partial, &G.dW2part, &G.dHpart, &G.P1buf, &G.G1buf};
     for (float **b : bufs) dev_free(*b);
     dev_free(G.mask1);
-    dev_free(G.mask2);
+    dev_free(G.mask2buf[0]);
+    dev_free(G.mask2buf[1]);
+    G.mask2 = nullptr;
 }
 
 void build_group(dgn_graph *g, Group &G) {
@@ -666,7 +676,9 @@ void build_group(dgn_graph *g, Group &G) {
     }
     G.mask2_words = (long long)K * n_j * P1;
     G.mask1 = dev_alloc<uint32_t>((size_t)G.mask1_words);
-    G.mask2 = dev_alloc<uint32_t>((size_t)G.mask2_words);
+    G.mask2buf[0] = dev_alloc<uint32_t>((size_t)G.mask2_words);
+    G.mask2buf[1] = dev_alloc<uint32_t>((size_t)G.mask2_words);
+    G.mask2 = G.mask2buf[0];
 
     // dense layer-2 kernels: persistent CTAs, one per (row block, slot of relations)
     // tensor-core versions (dense_tc.cu) unless DGN_DENSE_FFMA=1 asks for the CUDA-core kernels of dense.cu
@@ -775,7 +787,7 @@ struct StepDeps {
     std::vector<Dep> H, Z, dZ, dA; // per node type
 };
 
-void run_forward(dgn_graph *g, float rate, StepDeps &D) {
+void run_forward(dgn_graph *g, float rate, StepDeps &D, bool masks2_ready = false) {
     const int P1 = g->P1;
     const bool drop = rate > 0.f;
     const float keep = 1.f - rate;
@@ -786,14 +798,14 @@ void run_forward(dgn_graph *g, float rate, StepDeps &D) {
     fork_lanes(g);  // the side lanes start after everything queued so far (previous step's Adam, the per-step block);
                     // every call ends with them joined into lane 0, so nothing is pending there
     if (drop) {
-        if (g->two_lanes) {
+        if (g->two_lanes && !masks2_ready) {
             CUDA_CHECK(cudaEventRecord(g->mask_go, g->stream));  // after the join: last step's readers of mask2 are done
             CUDA_CHECK(cudaStreamWaitEvent(g->stream3, g->mask_go, 0));
             for (int side = 1; side >= 0; --side)  // the side groups' (small) masks first
                 for (auto &G : g->groups) {
                     if ((G.lane != 0) != (side == 1)) continue;
                     launch_gen_mask(G.mask2, G.mask2_words, (long long)G.n_j * g->d1, G.n_j * P1, G.rel_ids, kStreamDropout2, g->dyn_dev,
-                                    g->stream3);
+                                    0, g->stream3);
                     g->launches++;
                 }
             CUDA_CHECK(cudaEventRecord(g->mask_done, g->stream3));
@@ -819,13 +831,13 @@ void run_forward(dgn_graph *g, float rate, StepDeps &D) {
         } else {
             for (auto &G : g->groups) {
                 launch_gen_mask(G.mask2, G.mask2_words, (long long)G.n_j * g->d1, G.n_j * P1, G.rel_ids, kStreamDropout2, g->dyn_dev,
-                                g->stream);
+                                0, g->stream);
                 g->launches++;
             }
         }
     }
     bool mask_waited[dgn_graph::kMaxLanes];
-    for (bool &w : mask_waited) w = !(drop && g->two_lanes);
+    for (bool &w : mask_waited) w = !(drop && g->two_lanes) || masks2_ready;
     auto wait_mask2 = [&](int lane) {
         if (mask_waited[lane]) return;
         CUDA_CHECK(cudaStreamWaitEvent(lane_stream(g, lane), g->mask_done, 0));
@@ -993,7 +1005,7 @@ bool adam_fused(const dgn_graph *g, const Group &G, const AdamStep &adam) {
     return adam.alpha != 0.f && G.tstaged && !G.gen_feat && g->fuse_adam && !g->keep_grads;
 }
 
-void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam) {
+void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam, bool draw_ahead = false) {
     const int P1 = g->P1;
     const bool drop = rate > 0.f;
     const float scale = drop ? 1.f / (1.f - rate) : 1.f;
@@ -1133,7 +1145,23 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam) {
         }
         spmm_bwd(G, P1, g->grads + G.w1_off, (long long)G.Kl * G.F_j, drop ? G.mask1 : nullptr, adam_fused(g, G, adam));
     }
+    if (draw_ahead) {
+        // next step's layer-2 keep words into the OTHER buffer, on the mask stream, from the moment lane 0 has issued
+        // its last persistent kernel: the integer-ALU work runs beside the tensor-core dW2 kernel (few warps per SM)
+        // and the side lanes' tail instead of in front of the next step's first staged kernel
+        CUDA_CHECK(cudaEventRecord(g->ahead_go, g->stream));
+        CUDA_CHECK(cudaStreamWaitEvent(g->stream3, g->ahead_go, 0));
+        for (int side = 1; side >= 0; --side)
+            for (auto &G : g->groups) {
+                if ((G.lane != 0) != (side == 1)) continue;
+                launch_gen_mask(G.mask2buf[1 - g->mask_cur], G.mask2_words, (long long)G.n_j * g->d1, G.n_j * P1, G.rel_ids,
+                                kStreamDropout2, g->dyn_dev, 1, g->stream3);
+                g->launches++;
+            }
+        CUDA_CHECK(cudaEventRecord(g->ahead_done, g->stream3));
+    }
     for (auto &d : deferred_dw2) run_dw2(d.first, d.second);
+    if (draw_ahead) CUDA_CHECK(cudaStreamWaitEvent(g->stream, g->ahead_done, 0));
     join_lanes(g, false);
 }
 
@@ -1467,6 +1495,8 @@ extern "C" int dgn_graph_create(dgn_graph **out, int device, int n_types, const 
         CUDA_CHECK(cudaStreamCreateWithPriority(&g->stream3, cudaStreamNonBlocking, lo));
         CUDA_CHECK(cudaEventCreateWithFlags(&g->mask_go, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&g->mask_done, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&g->ahead_go, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&g->ahead_done, cudaEventDisableTiming));
     }
     g->own_stream = true;
     for (int i = 0; i < dgn_graph::kRing; ++i) CUDA_CHECK(cudaEventCreateWithFlags(&g->ring_ev[i], cudaEventDisableTiming));
@@ -1497,6 +1527,8 @@ extern "C" int dgn_graph_create(dgn_graph **out, int device, int n_types, const 
     g->fuse_adam = !(env && env[0] == '0');
     env = getenv("DGN_SINGLE_STREAM");
     g->two_lanes = !(env && env[0] == '1');
+    env = getenv("DGN_MASK_AHEAD");
+    g->mask_ahead = !(env && env[0] == '0');
     env = getenv("DGN_GATHER_ROWSUMS");
     g->gather_row_sums = env && env[0] == '1';
     env = getenv("DGN_CUDA_GRAPH");
@@ -1554,6 +1586,8 @@ extern "C" int dgn_graph_destroy(dgn_graph *g) {
     if (g->stream3) cudaStreamDestroy(g->stream3);
     if (g->mask_go) cudaEventDestroy(g->mask_go);
     if (g->mask_done) cudaEventDestroy(g->mask_done);
+    if (g->ahead_go) cudaEventDestroy(g->ahead_go);
+    if (g->ahead_done) cudaEventDestroy(g->ahead_done);
     delete g;
     DGN_API_END
 }
@@ -1624,6 +1658,7 @@ extern "C" int dgn_graph_finalize(dgn_graph *g) {
     }
     CUDA_CHECK(cudaStreamSynchronize(g->stream));
     drop_step_graphs(g);  // they hold the addresses of the old device layout
+    g->ahead_valid = false;  // rebuilt groups get fresh mask buffers
     for (auto &T : g->types) {
         free_csr(T.X);
         free_csr(T.Xt);
@@ -1899,10 +1934,10 @@ namespace {
 // while lane 0 is being captured into a CUDA graph).  Everything that differs between two steps is read by the
 // kernels from the per-step block in device memory (StepDyn), so the sequence of launches depends only on
 // (dropout on / off and its rate, update or not, gradients kept or not).
-void issue_train_step(dgn_graph *g, float dropout, bool apply_update) {
+void issue_train_step(dgn_graph *g, float dropout, bool apply_update, bool masks2_ready, bool draw_ahead) {
     cudaStream_t s = g->stream;
     StepDeps deps;
-    run_forward(g, dropout, deps);
+    run_forward(g, dropout, deps, masks2_ready);
     {
         for (int t = 0; t < g->n_types; ++t) consume(g, deps.Z[t], 0);
         PhaseScope ph(g, "decode");
@@ -1925,7 +1960,7 @@ void issue_train_step(dgn_graph *g, float dropout, bool apply_update) {
     }
     AdamStep adam;
     adam.alpha = apply_update ? 1.f : 0.f;  // only "is there an update": the coefficients are in the per-step block
-    run_backward(g, dropout, deps, adam);
+    run_backward(g, dropout, deps, adam, draw_ahead);
     if (apply_update) {
         PhaseScope ph(g, "adam");
         // every variable whose update was not fused into the kernel that produced its gradient
@@ -2003,6 +2038,12 @@ extern "C" int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t
     AdamStep mode;
     mode.alpha = apply_update ? 1.f : 0.f;
     for (auto &Gq : g->groups) Gq.w1_grad_stale = !Gq.gen_feat && adam_fused(g, Gq, mode);
+    // layer-2 keep words drawn ahead by the previous step?
+    const bool ahead_on = g->mask_ahead && g->two_lanes && dropout > 0.f;
+    const uint32_t thr = dropout_threshold(dropout);
+    const bool masks2_ready = ahead_on && g->ahead_valid && g->ahead_seed == seed && g->ahead_step == step && g->ahead_thr == thr;
+    if (masks2_ready) g->mask_cur ^= 1;
+    for (auto &Gq : g->groups) Gq.mask2 = Gq.mask2buf[g->mask_cur];
 
     // ---- the step itself: a CUDA graph replay when this configuration has been seen before
     bool done = false;
@@ -2013,7 +2054,8 @@ extern "C" int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t
                 for (int x = 0; x < 3; ++x) parity |= (int)(Gq.xch[x].stamp & 1u) << Gq.xch[x].id;
         uint32_t rate_bits;
         memcpy(&rate_bits, &dropout, sizeof(rate_bits));
-        dgn_graph::StepGraph &sg = g->step_graphs[std::make_tuple(rate_bits, apply_update ? 1 : 0, g->keep_grads ? 1 : 0, parity)];
+        const int mode_bits = (apply_update ? 1 : 0) | (masks2_ready ? 2 : 0) | (ahead_on ? 4 : 0) | (g->mask_cur << 3);
+        dgn_graph::StepGraph &sg = g->step_graphs[std::make_tuple(rate_bits, mode_bits, g->keep_grads ? 1 : 0, parity)];
         if (sg.exec == nullptr && sg.seen++ >= 1) {
             // second occurrence: capture (the first ran directly: lazy module loading and function attributes are done)
             const long long before = g->launches;
@@ -2021,7 +2063,7 @@ extern "C" int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t
             CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
             g->capturing = true;
             try {
-                issue_train_step(g, dropout, apply_update != 0);
+                issue_train_step(g, dropout, apply_update != 0, masks2_ready, ahead_on);
             } catch (...) {
                 g->capturing = false;
                 cudaStreamEndCapture(s, &graph);
@@ -2046,7 +2088,9 @@ extern "C" int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t
             done = true;
         }
     }
-    if (!done) issue_train_step(g, dropout, apply_update != 0);
+    if (!done) issue_train_step(g, dropout, apply_update != 0, masks2_ready, ahead_on);
+    g->ahead_valid = ahead_on;
+    g->ahead_seed = seed, g->ahead_step = step + 1, g->ahead_thr = thr;
     g->dzq_clean = g->n_types <= kMaxTypes;
     g->last_B = batch_size;
 

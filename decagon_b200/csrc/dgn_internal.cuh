@@ -291,8 +291,9 @@ struct MaskBatch {  // layer-1 keep bits of up to kMaxMaskBatch groups, one laun
     const int *rel_ids[kMaxMaskBatch];
 };
 void launch_gen_mask_multi(const MaskBatch &mb, uint32_t stream_id, const StepDyn *dyn, cudaStream_t s);
+// step_offset: the masks of step dyn->step + step_offset (1: drawn ahead, while the current step's backward finishes)
 void launch_gen_mask(uint32_t *words, long long n_words, long long bits_per_rel, int words_per_rel_or_0, const int *rel_ids,
-                     uint32_t stream_id, const StepDyn *dyn, cudaStream_t s);
+                     uint32_t stream_id, const StepDyn *dyn, uint32_t step_offset, cudaStream_t s);
 int dense_row_block(int D1, int which);
 void launch_project(const DenseArgs &a, int D1, int D2, cudaStream_t s);
 void launch_dw2(const DenseArgs &a, int D1, int D2, cudaStream_t s);

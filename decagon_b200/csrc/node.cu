@@ -243,9 +243,9 @@ __device__ __forceinline__ void mask_word(long long w, uint32_t *__restrict__ wo
 // register slots to the L2-bound gather kernels of the other stream lane that run beside it.
 __global__ void __launch_bounds__(256) gen_mask_kernel(uint32_t *__restrict__ words, long long n_words, long long bits_per_rel,
                                                        int words_per_rel, const int *__restrict__ rel_ids, uint32_t stream_id,
-                                                       const StepDyn *__restrict__ dyn, long long total_bits) {
+                                                       const StepDyn *__restrict__ dyn, uint32_t step_offset, long long total_bits) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    const uint32_t step = dyn->step, seed_lo = dyn->seed_lo, seed_hi = dyn->seed_hi, threshold = dyn->threshold;
+    const uint32_t step = dyn->step + step_offset, seed_lo = dyn->seed_lo, seed_hi = dyn->seed_hi, threshold = dyn->threshold;
     for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < n_words; w += stride)
         mask_word(w, words, bits_per_rel, words_per_rel, rel_ids, stream_id, step, seed_lo, seed_hi, threshold, total_bits);
 }
@@ -400,7 +400,7 @@ void launch_gen_mask_multi(const MaskBatch &mb, uint32_t stream_id, const StepDy
 }
 
 void launch_gen_mask(uint32_t *words, long long n_words, long long bits_per_rel, int words_per_rel, const int *rel_ids,
-                     uint32_t stream_id, const StepDyn *dyn, cudaStream_t s) {
+                     uint32_t stream_id, const StepDyn *dyn, uint32_t step_offset, cudaStream_t s) {
     if (n_words == 0) return;
     const long long total_bits = n_words * 32;  // packed mode: caller rounds the word count up
     static int ctas_per_sm = 0;  // DGN_MASK_CTAS: CTAs per SM the layer-2 mask kernel may occupy (default 3)
@@ -409,7 +409,7 @@ void launch_gen_mask(uint32_t *words, long long n_words, long long bits_per_rel,
         ctas_per_sm = e && atoi(e) > 0 ? atoi(e) : 3;
     }
     dim3 grid((unsigned)std::min<long long>((n_words + 255) / 256, 148LL * ctas_per_sm)), block(256);
-    gen_mask_kernel<<<grid, block, 0, s>>>(words, n_words, bits_per_rel, words_per_rel, rel_ids, stream_id, dyn, total_bits);
+    gen_mask_kernel<<<grid, block, 0, s>>>(words, n_words, bits_per_rel, words_per_rel, rel_ids, stream_id, dyn, step_offset, total_bits);
     CUDA_CHECK(cudaGetLastError());
 }
 
