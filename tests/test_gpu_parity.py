@@ -338,7 +338,7 @@ def test_general_sparse_features(graph_kind):
 
 @pytest.mark.parametrize('env', [{'DGN_SINGLE_STREAM': '1'}, {'DGN_PROJECT_SS': '1'}, {'DGN_FUSE_ADAM': '0'},
                                  {'DGN_DISABLE_TSTAGED': '1'}, {'DGN_MASK_CTAS': '1'}, {'DGN_CUDA_GRAPH': '0'},
-                                 {'DGN_SIDE_LANES': '4'}, {'DGN_GATHER_ROWSUMS': '1'}, {'DGN_MASK_AHEAD': '0'}])
+                                 {'DGN_SIDE_LANES': '4'}, {'DGN_GATHER_ROWSUMS': '1'}, {'DGN_MASK_AHEAD': '1'}])
 def test_alternate_code_paths(env):
     """The switches that select the non-default kernels / schedules (one stream instead of the lanes + mask stream,
     the shared-memory projection instead of the tensor-memory one, unfused Adam, gather-path backward) give the
@@ -497,14 +497,16 @@ def test_cuda_graph_replay_is_bit_identical():
     block StepDyn) against the same steps issued kernel by kernel (DGN_CUDA_GRAPH=0): losses, negatives and every
     parameter bit for bit over steps that change relation group, dropout rate and update mode."""
     c = Case(common.mini_poly(n_types=10, seed=31), batch_size=64)
-    graphed = c.engine()   # defaults: graph replay, layer-2 keep words drawn one step ahead
+    os.environ['DGN_MASK_AHEAD'] = '1'   # graph replay (default) + layer-2 keep words drawn one step ahead
+    try:
+        graphed = c.engine()
+    finally:
+        del os.environ['DGN_MASK_AHEAD']
     os.environ['DGN_CUDA_GRAPH'] = '0'
-    os.environ['DGN_MASK_AHEAD'] = '0'
     try:
         direct = c.engine()
     finally:
         del os.environ['DGN_CUDA_GRAPH']
-        del os.environ['DGN_MASK_AHEAD']
     for e in (graphed, direct):
         e.reset_optimizer()
     plan = [(0.1, True)] * 6 + [(0.0, True)] * 3 + [(0.1, False)] * 3 + [(0.1, True)] * 4
