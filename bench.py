@@ -210,7 +210,9 @@ def workload_config(args, inputs):
             'n_proteins': inputs.n_nodes[0], 'n_drugs': inputs.n_nodes[1],
             'relation_matrices': sum(inputs.edge_types.values()), 'hidden': [HYPER['hidden1'], HYPER['hidden2']],
             'batch': HYPER['batch_size'], 'dropout': HYPER['dropout'], 'loss': 'hinge', 'optimizer': 'adam(tf1)',
-            'scale': args.scale, 'l2': 'per-step working set (>4 GB) exceeds the 126 MB L2; no explicit flush'}
+            'scale': args.scale,
+            'l2': ('per-step working set (>4 GB) exceeds the 126 MB L2; no explicit flush' if args.config == 'poly' else
+                   'working set ~1 MB, L2-resident by nature: latency-bound, steps/s and parity only, no roofline claim')}
 
 
 def construct_placeholders(edge_types):
