@@ -80,7 +80,14 @@ int dgn_sampler_thresholds(const double *degrees, int32_t n, uint32_t *threshold
 /* ---- graph lifetime --------------------------------------------------------------------- */
 
 /* DecagonModel.__init__ (model.py:48-62): edge_types -> groups / K, num_feat -> feat_dim,
- * FLAGS.hidden1 / hidden2 (model.py:68,80).  hidden1 and hidden2 must be multiples of 32. */
+ * FLAGS.hidden1 / hidden2 (model.py:68,80).
+ * Supported: hidden1 in {32, 64, 128}, hidden2 == 32 (anything else: DGN_ERR_UNSUPPORTED).
+ * NOT supported: a per-relation activation inside the graph-convolution layers.  GraphConvolutionSparseMulti /
+ * GraphConvolutionMulti default to act = tf.nn.relu applied to every relation's product BEFORE add_n
+ * (layers.py:73,91,99,115); DecagonModel always constructs them with act = lambda x: x (model.py:71,82) and applies ONE
+ * relu after the sum over the groups of a node type (model.py:74-75), which is what this library computes.  Summing
+ * the relations in registers is only possible because nothing non-linear sits between a relation's product and the
+ * sum; the Python layer classes raise NotImplementedError for any other act. */
 int dgn_graph_create(dgn_graph **out, int device, int n_types, const int32_t *n_nodes, const int32_t *feat_dim,
                      int n_groups, const int32_t *group_ij, const int32_t *group_K, const int32_t *group_decoder,
                      int hidden1, int hidden2);
