@@ -345,3 +345,34 @@ def test_sparse_relation_masks_equal_the_dense_reference_formula():
             want = sp.csr_matrix(np.multiply(dense_masks[rel], mats[rel].toarray()))   # _applyMask (:187-190)
             assert (got[rel] != want).nnz == 0 and got[rel].nnz == want.nnz
             assert np.array_equal(got[rel].indptr, want.indptr) and np.array_equal(got[rel].indices, want.indices)
+
+
+def test_feed_dict_token_semantics():
+    """minibatch.FeedDict: update_feed_dict stamps the token that lets Session skip the walk over every adjacency
+    tuple; only replacing a sparse (adjacency / feature) entry clears it; plain dicts never carry one."""
+    from decagon_b200 import tf_compat as tf
+    from decagon_b200.deep.minibatch import FeedDict
+    inputs = datasets.toy_graph()
+    ph = {'batch': tf.placeholder(tf.int32), 'batch_edge_type_idx': tf.placeholder(tf.int32),
+          'batch_row_edge_type': tf.placeholder(tf.int32), 'batch_col_edge_type': tf.placeholder(tf.int32),
+          'dropout': tf.placeholder_with_default(0., shape=())}
+    ph.update({'adj_mats_%d,%d,%d' % (i, j, k): tf.sparse_placeholder(tf.float32)
+               for i, j in inputs.edge_types for k in range(inputs.edge_types[i, j])})
+    ph.update({'feat_%d' % i: tf.sparse_placeholder(tf.float32) for i, _ in inputs.edge_types})
+    np.random.seed(0)
+    it = EdgeMinibatchIterator(inputs.adj_mats, inputs.feat, inputs.edge_types, {}, batch_size=512, val_test_size=0.05)
+    fd = it.next_minibatch_feed_dict(ph)
+    assert isinstance(fd, FeedDict) and isinstance(fd, dict) and fd.graph_token is None and len(fd) == 4
+    fd = it.update_feed_dict(fd, 0.1, ph)
+    assert fd.graph_token == (id(it), id(ph)) and len(fd) == 4 + 10 + 2 + 1
+    assert fd[ph['adj_mats_1,1,3']] is it.adj_train[1, 1][3] and fd[ph['dropout']] == 0.1
+    fd[ph['dropout']] = 0.0
+    fd[ph['batch_edge_type_idx']] = 3
+    assert fd.graph_token is not None
+    fd[ph['feat_0']] = it.feat[0]
+    assert fd.graph_token is None
+    plain = it.update_feed_dict(dict(it.next_minibatch_feed_dict(ph)), 0.1, ph)
+    assert type(plain) is dict and len(plain) == 17
+    other = it.update_feed_dict(it.next_minibatch_feed_dict(ph), 0.1, ph)
+    other.update({ph['dropout']: 0.5})
+    assert other.graph_token is None
