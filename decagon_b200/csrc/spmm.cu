@@ -46,7 +46,8 @@ __global__ void __launch_bounds__(256) spmm_seg_kernel(const SpmmArgs a) {
         if (a.seg_row != nullptr) {
             row = __ldg(a.seg_row + seg);
             begin = __ldg(a.seg_begin + seg);
-            end = min(begin + a.seg_len, __ldg(a.rowptr + row + 1));
+            // the segment ends where the row's next segment begins (hub rows have longer segments than seg_len)
+            end = (seg + 1 < a.n_seg && __ldg(a.seg_row + seg + 1) == row) ? __ldg(a.seg_begin + seg + 1) : __ldg(a.rowptr + row + 1);
             single = (__ldg(a.row_seg_ptr + row + 1) - __ldg(a.row_seg_ptr + row)) == 1;
         } else {
             row = seg;

@@ -76,18 +76,76 @@ def _contains(pair, edges):
 
 
 class FeedDict(dict):
-    """A plain feed dict plus ``graph_token``: set by ``update_feed_dict`` when every adjacency / feature entry
-    is the iterator's own tuple, cleared as soon as the caller replaces one of them."""
+    """A feed dict whose ~2000 adjacency / feature entries are attached LAZILY.
+
+    ``update_feed_dict`` (called every step by the reference's trainer) adds the same 1934 tuples to a fresh dict
+    each time -- 48 us of hashing at the polypharmacy shape that nobody looks at when the session already holds the
+    graph.  Here it attaches the iterator's shared ``{placeholder: tuple}`` mapping as ``_pending`` together with
+    ``graph_token`` (which tells ``Session`` that every such entry is the iterator's own tuple); the entries are
+    merged into the dict the first time anything could observe their absence: a lookup miss, ``in``, ``len``,
+    iteration, ``keys / values / items / get / copy / pop`` and ``dict(fd)`` (which goes through ``keys`` because
+    ``__iter__`` is overridden).  Replacing a sparse entry by hand clears the token."""
     graph_token = None
+    _pending = None
+
+    def _materialise(self):
+        pending = self._pending
+        if pending is not None:
+            self._pending = None
+            for k, v in pending.items():   # explicit entries win over the attached ones
+                if not dict.__contains__(self, k):
+                    dict.__setitem__(self, k, v)
+
+    def attach(self, entries, token):
+        self._materialise()
+        self._pending = entries
+        self.graph_token = token
+
+    def __missing__(self, key):
+        if self._pending is not None:
+            self._materialise()
+            return dict.__getitem__(self, key)
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or (self._pending is not None and key in self._pending)
+
+    def get(self, key, default=None):
+        if dict.__contains__(self, key):
+            return dict.__getitem__(self, key)
+        if self._pending is not None and key in self._pending:
+            return self._pending[key]
+        return default
 
     def __setitem__(self, key, value):
         if getattr(key, 'sparse', False):
+            self._materialise()
             self.graph_token = None
         dict.__setitem__(self, key, value)
 
     def update(self, *args, **kwargs):
+        self._materialise()
         self.graph_token = None
         dict.update(self, *args, **kwargs)
+
+    def _full(name):
+        def method(self, *args, **kwargs):
+            self._materialise()
+            return getattr(dict, name)(self, *args, **kwargs)
+        method.__name__ = name
+        return method
+
+    for _name in ('__len__', '__iter__', 'keys', 'values', 'items', 'pop', 'popitem', 'setdefault', '__delitem__',
+                  '__eq__', '__ne__', '__repr__', '__reversed__', '__or__', '__ror__'):
+        locals()[_name] = _full(_name)
+    del _name, _full
+    __hash__ = None
+
+    def copy(self):
+        self._materialise()
+        out = FeedDict(dict.copy(self))
+        out.graph_token = self.graph_token
+        return out
 
 
 class EdgeMinibatchIterator(object):
@@ -257,11 +315,12 @@ class EdgeMinibatchIterator(object):
         what lets ``decagon_b200.session.Session`` keep them resident on the device; a ``FeedDict``
         (what ``batch_feed_dict`` returns) also carries a token naming this iterator's graph, so the
         session does not have to compare the 1932 tuples of the polypharmacy shape on every run."""
-        dict.update(feed_dict, self._graph_feed(placeholders))
-        dict.__setitem__(feed_dict, placeholders['dropout'], dropout)
         if isinstance(feed_dict, FeedDict):
-            feed_dict.graph_token = (id(self), id(placeholders))
+            feed_dict.attach(self._graph_feed(placeholders), (id(self), id(placeholders)))
             feed_dict._graph_owner = self  # keeps id(self) unique while the feed dict lives
+        else:
+            dict.update(feed_dict, self._graph_feed(placeholders))
+        dict.__setitem__(feed_dict, placeholders['dropout'], dropout)
         return feed_dict
 
     def batch_feed_dict(self, batch_edges, batch_edge_type, placeholders):
@@ -286,7 +345,11 @@ class EdgeMinibatchIterator(object):
             elif slot == 2 and period == 4:
                 self.current_edge_type_idx = self.edge_type2idx[1, 0, 0]
             elif len(self.freebatch_edge_types) > 0:
-                self.current_edge_type_idx = np.random.choice(self.freebatch_edge_types)
+                # np.random.choice(list) of the reference (minibatch.py:292) draws randint(0, len) on the same legacy
+                # stream after converting the list to an array (115 us for 1929 relations); the direct draw is
+                # bit-identical (tests/test_host.py::test_choice_is_randint) and takes 4 us
+                free = self.freebatch_edge_types
+                self.current_edge_type_idx = free[np.random.randint(0, len(free))]
             else:
                 self.current_edge_type_idx = self.edge_type2idx[0, 0, 0]
                 self.iter = 0

@@ -376,3 +376,37 @@ def test_feed_dict_token_semantics():
     other = it.update_feed_dict(it.next_minibatch_feed_dict(ph), 0.1, ph)
     other.update({ph['dropout']: 0.5})
     assert other.graph_token is None
+
+
+def test_choice_is_randint():
+    """The schedule draws relation r = free[randint(0, len(free))]; the reference writes np.random.choice(free)
+    (minibatch.py:292).  Same values, same generator state afterwards."""
+    for n in (1, 2, 7, 1929):
+        free = list(range(5, 5 + n))
+        np.random.seed(9)
+        a = [np.random.choice(free) for _ in range(50)]
+        sa = np.random.get_state()
+        np.random.seed(9)
+        b = [free[np.random.randint(0, len(free))] for _ in range(50)]
+        sb = np.random.get_state()
+        assert a == b and sa[2] == sb[2] and np.array_equal(sa[1], sb[1])
+
+
+def test_lazy_feed_dict_behaves_like_a_dict():
+    from decagon_b200.deep.minibatch import FeedDict
+    base = {('adj', k): (k, k) for k in range(50)}
+    fd = FeedDict({'batch': 1, 'idx': 2})
+    fd.attach(base, 'token')
+    dict.__setitem__(fd, 'dropout', 0.1)
+    assert fd['batch'] == 1 and ('adj', 3) in fd and fd.get(('adj', 4)) == (4, 4) and fd.get('nope', 7) == 7
+    assert fd._pending is not None                      # nothing forced the merge yet
+    assert fd[('adj', 7)] == (7, 7) and fd._pending is None   # a lookup miss merges
+    fd2 = FeedDict({'batch': 1})
+    fd2.attach(base, 'token')
+    assert len(fd2) == 51 and len(dict(fd2)) == 51 and set(fd2.keys()) == set(base) | {'batch'}
+    fd3 = FeedDict({'batch': 1, ('adj', 0): 'mine'})
+    fd3.attach(base, 'token')
+    assert dict(fd3)[('adj', 0)] == 'mine' and fd3.copy().graph_token == 'token'
+    with pytest.raises(KeyError):
+        fd3['missing']
+    assert {**fd2}['batch'] == 1 and sorted(k for k in fd2 if k != 'batch') == sorted(base)
