@@ -61,7 +61,6 @@ DevCsr upload_csr(const HostCsr &h) {
 }
 
 // every_row: rows without non-zeros still get one (empty) segment so that their result is written
-constexpr int kMaxSegsPerRow = 16;
 SegTable build_segments(const HostCsr &h, int seg_len, bool every_row) {
     SegTable t;
     t.seg_len = seg_len;
@@ -77,10 +76,9 @@ SegTable build_segments(const HostCsr &h, int seg_len, bool every_row) {
     for (int r = 0; r < h.n_rows; ++r) {
         const int b = h.rowptr[r], e = h.rowptr[r + 1];
         int n = 0;
-        // a row is cut into at most kMaxSegsPerRow pieces: hub rows get longer segments, so that the ordered sum over
-        // a row's partials (epilogue / seg_reduce, one warp per row) stays short
-        const int len = std::max(seg_len, ((e - b + kMaxSegsPerRow - 1) / kMaxSegsPerRow + 7) / 8 * 8);
-        for (int s = b; s < e; s += len) {
+        // (capping the segments per row at 16 -- longer segments for hub rows, shorter ordered sums in the epilogue --
+        // was measured: the gather kernels get a tail, 80 -> 138 us for the PPI forward; not kept)
+        for (int s = b; s < e; s += seg_len) {
             seg_row.push_back(r);
             seg_begin.push_back(s);
             ++n;
