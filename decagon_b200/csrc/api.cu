@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <memory>
 #include <numeric>
 #include <queue>
@@ -446,6 +447,8 @@ struct dgn_graph {
     long long graph_replays = 0;
     long long groups_rebuilt = 0;  // build_group calls so far (tests: incremental finalize)
     float *pos_out = nullptr, *negs_out = nullptr, *loss_dev = nullptr, *loss_host = nullptr;
+    uint32_t step_seq = 0;           // serial number of the last issued training step
+    bool early_loss = true;          // DGN_SYNC_LOSS=1: dgn_train_step waits for the whole step before it returns the loss
     float *decode_scratch = nullptr;
     unsigned *decode_ticket = nullptr;
     int last_B = 0;
@@ -1503,7 +1506,7 @@ extern "C" int dgn_graph_create(dgn_graph **out, int device, int n_types, const 
     }
     g->own_stream = true;
     for (int i = 0; i < dgn_graph::kRing; ++i) CUDA_CHECK(cudaEventCreateWithFlags(&g->ring_ev[i], cudaEventDisableTiming));
-    g->loss_dev = dev_alloc<float>(1);
+    g->loss_dev = dev_alloc<float>(2);  // [loss, serial number of the step]
     g->exchange_error = dev_alloc<int>(1);
     CUDA_CHECK(cudaMemset(g->exchange_error, 0, sizeof(int)));
     CUDA_CHECK(cudaMallocHost(&g->exchange_error_host, sizeof(int)));
@@ -1512,7 +1515,9 @@ extern "C" int dgn_graph_create(dgn_graph **out, int device, int n_types, const 
     g->decode_scratch = dev_alloc<float>((size_t)kDecodeCtas * (32 * 32 + 1));
     g->decode_ticket = dev_alloc<unsigned>(1);
     CUDA_CHECK(cudaMemset(g->decode_ticket, 0, sizeof(unsigned)));
-    CUDA_CHECK(cudaMallocHost(&g->loss_host, sizeof(float)));
+    CUDA_CHECK(cudaMallocHost(&g->loss_host, 2 * sizeof(float)));
+    g->loss_host[0] = g->loss_host[1] = 0.f;
+    if (const char *e = getenv("DGN_SYNC_LOSS")) g->early_loss = e[0] != '1';
     for (int t = 0; t < n_types; ++t) {
         NodeType &T = g->types[t];
         T.H = dev_alloc<float>(panel_floats(g->P1, T.n));
@@ -1937,7 +1942,7 @@ namespace {
 // while lane 0 is being captured into a CUDA graph).  Everything that differs between two steps is read by the
 // kernels from the per-step block in device memory (StepDyn), so the sequence of launches depends only on
 // (dropout on / off and its rate, update or not, gradients kept or not).
-void issue_train_step(dgn_graph *g, float dropout, bool apply_update, bool masks2_ready, bool draw_ahead) {
+void issue_train_step(dgn_graph *g, float dropout, bool apply_update, bool masks2_ready, bool draw_ahead, bool early_loss) {
     cudaStream_t s = g->stream;
     StepDeps deps;
     run_forward(g, dropout, deps, masks2_ready);
@@ -1948,6 +1953,12 @@ void issue_train_step(dgn_graph *g, float dropout, bool apply_update, bool masks
             CUDA_CHECK(cudaMemsetAsync(g->grads + g->dec_off, 0, (g->n_params - g->dec_off) * sizeof(float), s));
         launch_decode(g->dyn_dev, s);
         g->launches++;
+        if (early_loss) {
+            // the loss is final once decode has run: it goes to pinned host memory now, together with the step's serial
+            // number; the host polls for that number and returns from dgn_train_step while the backward pass and the
+            // optimizer are still running (every later call is ordered behind them on the stream)
+            CUDA_CHECK(cudaMemcpyAsync(g->loss_host, g->loss_dev, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+        }
         if (g->n_types <= kMaxTypes) {
             FixedBatch fb = {};
             for (auto &T : g->types) fb.q[fb.count] = T.dZq, fb.out[fb.count] = T.dZ, fb.n[fb.count] = (size_t)panel_floats(1, T.n), fb.count++;
@@ -2012,6 +2023,7 @@ extern "C" int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t
     const int slot = begin_step(g, dropout, seed, step, 3);
     unsigned char *host = g->step_host[slot];
     StepDyn *h = reinterpret_cast<StepDyn *>(host);
+    h->seq = ++g->step_seq;
     if (apply_update) {
         // TF 1.8 ApplyAdam: alpha = lr * sqrt(1 - beta2^t) / (1 - beta1^t), float32
         h->alpha = learning_rate * sqrtf(1.f - g->b2p) / (1.f - g->b1p);
@@ -2049,6 +2061,7 @@ extern "C" int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t
     for (auto &Gq : g->groups) Gq.mask2 = Gq.mask2buf[g->mask_cur];
 
     // ---- the step itself: a CUDA graph replay when this configuration has been seen before
+    const bool early = loss_out != nullptr && g->early_loss && !g->timing;
     bool done = false;
     if (g->use_graphs && !g->timing) {
         int parity = 0;
@@ -2057,7 +2070,7 @@ extern "C" int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t
                 for (int x = 0; x < 3; ++x) parity |= (int)(Gq.xch[x].stamp & 1u) << Gq.xch[x].id;
         uint32_t rate_bits;
         memcpy(&rate_bits, &dropout, sizeof(rate_bits));
-        const int mode_bits = (apply_update ? 1 : 0) | (masks2_ready ? 2 : 0) | (ahead_on ? 4 : 0) | (g->mask_cur << 3);
+        const int mode_bits = (apply_update ? 1 : 0) | (masks2_ready ? 2 : 0) | (ahead_on ? 4 : 0) | (g->mask_cur << 3) | (early ? 16 : 0);
         dgn_graph::StepGraph &sg = g->step_graphs[std::make_tuple(rate_bits, mode_bits, g->keep_grads ? 1 : 0, parity)];
         if (sg.exec == nullptr && sg.seen++ >= 1) {
             // second occurrence: capture (the first ran directly: lazy module loading and function attributes are done)
@@ -2066,7 +2079,7 @@ extern "C" int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t
             CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
             g->capturing = true;
             try {
-                issue_train_step(g, dropout, apply_update != 0, masks2_ready, ahead_on);
+                issue_train_step(g, dropout, apply_update != 0, masks2_ready, ahead_on, early);
             } catch (...) {
                 g->capturing = false;
                 cudaStreamEndCapture(s, &graph);
@@ -2091,7 +2104,7 @@ extern "C" int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t
             done = true;
         }
     }
-    if (!done) issue_train_step(g, dropout, apply_update != 0, masks2_ready, ahead_on);
+    if (!done) issue_train_step(g, dropout, apply_update != 0, masks2_ready, ahead_on, early);
     g->ahead_valid = ahead_on;
     g->ahead_seed = seed, g->ahead_step = step + 1, g->ahead_thr = thr;
     g->dzq_clean = g->n_types <= kMaxTypes;
@@ -2101,7 +2114,20 @@ extern "C" int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t
         g->b1p *= g->beta1;
         g->b2p *= g->beta2;
     }
-    if (loss_out) {
+    if (loss_out && early) {
+        // session.run([opt_op, cost]) returns when the COST is known; the update it queued is complete before any
+        // later call can observe a variable (same stream)
+        const volatile uint32_t *seq_host = reinterpret_cast<const volatile uint32_t *>(g->loss_host + 1);
+        for (long long spin = 0; *seq_host != g->step_seq; ++spin) {
+            if ((spin & 0xfff) == 0xfff) {  // every 4096 polls: did the stream stop (error, or done without our number)?
+                cudaError_t e = cudaStreamQuery(s);
+                if (e == cudaSuccess && *seq_host != g->step_seq) DGN_FAIL(DGN_ERR_CUDA, "the step finished without delivering its loss");
+                if (e != cudaSuccess && e != cudaErrorNotReady) DGN_FAIL(DGN_ERR_CUDA, "training step failed: %s", cudaGetErrorString(e));
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        *loss_out = *const_cast<const volatile float *>(g->loss_host);
+    } else if (loss_out) {
         CUDA_CHECK(cudaMemcpyAsync(g->loss_host, g->loss_dev, sizeof(float), cudaMemcpyDeviceToHost, s));
         CUDA_CHECK(cudaStreamSynchronize(s));
         check_exchange(g);

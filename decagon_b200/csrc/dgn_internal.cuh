@@ -243,6 +243,8 @@ constexpr int kMaxExchanges = 16;  // flag slots per source rank
 struct StepDyn {
     uint32_t step, seed_lo, seed_hi, threshold;  // dropout streams: Philox key / counter words, keep threshold
     float alpha, omb1, omb2, eps;                // TF1 Adam: alpha = lr sqrt(1 - b2^t) / (1 - b1^t)
+    uint32_t seq;                                // serial number of the step: stored next to the loss, so that the host can tell
+                                                 // this step's loss from the previous one in its pinned buffer
     uint32_t stamp[kMaxExchanges];               // multi-GPU: the stamp each exchange publishes / waits for this step
     DecodeArgs dec;                              // minibatch, relation, decoder variables, loss
 };

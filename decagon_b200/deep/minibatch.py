@@ -17,6 +17,8 @@ Reference quirks that are kept on purpose:
 * a transposed twin re-uses its original's normalised tuple with the coordinates
   flipped and the values untouched (``minibatch.py:141-149``).
 """
+import os
+
 import numpy as np
 import scipy.sparse as sp
 
@@ -73,6 +75,9 @@ def _contains(pair, edges):
     if edges.size == 0:
         return False
     return bool(np.any((edges[:, 0] == pair[0]) & (edges[:, 1] == pair[1])))
+
+
+_EAGER_FEED = os.environ.get('DGN_EAGER_FEED') == '1'  # A/B switch: copy the entries every step like a plain dict
 
 
 class FeedDict(dict):
@@ -318,6 +323,8 @@ class EdgeMinibatchIterator(object):
         if isinstance(feed_dict, FeedDict):
             feed_dict.attach(self._graph_feed(placeholders), (id(self), id(placeholders)))
             feed_dict._graph_owner = self  # keeps id(self) unique while the feed dict lives
+            if _EAGER_FEED:
+                feed_dict._materialise()
         else:
             dict.update(feed_dict, self._graph_feed(placeholders))
         dict.__setitem__(feed_dict, placeholders['dropout'], dropout)
