@@ -160,7 +160,10 @@ int dgn_encoder_forward(dgn_graph *g, float dropout, uint64_t seed, uint32_t ste
  * negatives == NULL: sampled on device from relation r's unigram^0.75 table (optimizer.py:36-49);
  * otherwise int64[B] row-node indices are used as given (parity runs).
  * apply_update == 0 computes loss and gradients only (optimizer.grads_vars).
- * loss_out (host float, may be NULL) is written after the step completes. */
+ * loss_out (host float, may be NULL) is written before the call returns.  The call returns as soon as the LOSS has
+ * reached the host (right after the decode kernel); the backward pass and the optimizer it queued are still running
+ * and complete before any later call on this handle can observe a variable, gradient or embedding (one stream order;
+ * dgn_sync waits for everything).  DGN_SYNC_LOSS=1 makes the call wait for the whole step instead. */
 int dgn_train_step(dgn_graph *g, int r, const int32_t *batch, int32_t batch_size, const int64_t *negatives,
                    int loss_kind, float margin, float neg_weight, float learning_rate, float dropout, uint64_t seed,
                    uint32_t step, int apply_update, float *loss_out);
