@@ -366,9 +366,10 @@ def run_ours(args):
     # (1) device-resident throughput: graph, parameters and optimizer state live in HBM; the only
     # per-step input is the 4 KB batch index block; CUDA events on the library's stream
     batches = [as_batch(feed()) for _ in range(args.steps)]
-    for r, batch in [as_batch(feed()) for _ in range(3)]:
+    for r, batch in [as_batch(feed()) for _ in range(6)]:
         # warm the launch configuration of this leg too: a step that does not fetch the loss replays a different CUDA
-        # graph than the Session steps above (no early loss copy); its first two occurrences issue / capture it
+        # graph than the Session steps above (no early loss copy); its first two occurrences issue / capture it, and
+        # with several ranks there are two such graphs (the exchange buffers alternate)
         eng.train_step(r, batch, step=step, want_loss=False, **kw)
         step += 1
     barrier()
