@@ -407,7 +407,7 @@ def run_ours(args):
     alg = algorithmic_bytes(inputs, it, HYPER['hidden1'], HYPER['hidden2'],
                             (lambda g, k: eng.relation_owner(flat_index[(g, k)]) in (-1, rank)) if world > 1 else None)
     phases = {}
-    names = list(alg) + ['project', 'dw2', 'dh', 'mask', 'epilogue', 'decode', 'adam']
+    names = list(alg) + ['project', 'dw2', 'dh', 'mask', 'epilogue', 'decode', 'adam', 'exchange']
     names += ['%s/g%d' % (n, gi) for n in ('project', 'dw2', 'dh') for gi in range(len(inputs.edge_types))]
     for name in names:
         ms, n = eng.timing_get(name)

@@ -965,8 +965,11 @@ void run_forward(dgn_graph *g, float rate, StepDeps &D, bool masks2_ready = fals
             } else {
                 spmm_fwd(G, g->params + G.w1_off, P1, (long long)G.Kl * G.F_j, G.part1, G.slots1, G.wstart1, drop ? G.mask1 : nullptr);
             }
-            if (G.partitioned && G.staged) exchange(g, G, 0, G.part1, G.slots1.n_slots, lane_stream(g, G.lane));
-            else if (G.partitioned) exchange(g, G, 0, G.rows1, 1, lane_stream(g, G.lane));
+        }
+        if (G.partitioned) {  // its own phase: the wait for the slowest rank is not SpMM time
+            PhaseScope ph(g, "exchange", gi, G.lane);
+            if (G.staged) exchange(g, G, 0, G.part1, G.slots1.n_slots, lane_stream(g, G.lane));
+            else exchange(g, G, 0, G.rows1, 1, lane_stream(g, G.lane));
         }
         produced(g, D.S1[gi], G.lane);
     }
@@ -991,8 +994,11 @@ void run_forward(dgn_graph *g, float rate, StepDeps &D, bool masks2_ready = fals
         {
             PhaseScope ph(g, "spmm_fwd2", gi, G.lane);
             spmm_fwd(G, G.P2, 1, (long long)G.Kl * G.n_j, G.part2, G.slots2, G.wstart2, nullptr);
-            if (G.partitioned && G.staged) exchange(g, G, 1, G.part2, G.slots2.n_slots, lane_stream(g, G.lane));
-            else if (G.partitioned) exchange(g, G, 1, G.rows2, 1, lane_stream(g, G.lane));
+        }
+        if (G.partitioned) {
+            PhaseScope ph(g, "exchange", gi, G.lane);
+            if (G.staged) exchange(g, G, 1, G.part2, G.slots2.n_slots, lane_stream(g, G.lane));
+            else exchange(g, G, 1, G.rows2, 1, lane_stream(g, G.lane));
         }
         produced(g, D.S2[gi], G.lane);
     }
@@ -1099,7 +1105,10 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam, b
             if (G.dense_tc) launch_dh_tc(a, g->d1, s);
             else launch_dh(a, g->d1, g->d2, s);
             g->launches++;
-            if (G.partitioned) exchange(g, G, 2, G.dHpart, G.slots_dh, s);
+        }
+        if (G.partitioned) {
+            PhaseScope ph(g, "exchange", gi, G.lane);
+            exchange(g, G, 2, G.dHpart, G.slots_dh, s);
         }
         produced(g, D.dH[gi], G.lane);
     }

@@ -225,8 +225,8 @@ int dgn_sync(dgn_graph *g);
 /* CUDA-event time in ms (events recorded on the library's own stream) of phase `name`
  * accumulated since the last dgn_timing_reset and the number of brackets summed; `name` is a
  * PREFIX.  Phases: "mask", "spmm_fwd1/g<group>", "spmm_fwd2/g<group>", "spmm_bwd2/g<group>",
- * "spmm_bwd1/g<group>", "project/g<group>", "dw2/g<group>", "dh/g<group>", "decode", "adam",
- * "epilogue", "predict".
+ * "spmm_bwd1/g<group>", "project/g<group>", "dw2/g<group>", "dh/g<group>", "exchange/g<group>" (multi-GPU: publish + wait
+ * for every peer), "decode", "adam", "epilogue", "predict".
  * dgn_launch_count: kernels launched by the library since the last dgn_timing_reset. */
 int dgn_timing_enable(dgn_graph *g, int enable);
 int dgn_timing_reset(dgn_graph *g);
