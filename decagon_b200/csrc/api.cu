@@ -378,6 +378,11 @@ struct Phase {
 struct dgn_graph {
     int device = 0, n_sm = 148;
     int n_types = 0, n_groups = 0, R = 0, d1 = 0, d2 = 0, P1 = 0;
+    // hidden2 as the caller passed it (model.py:80 takes any FLAGS.hidden2); the device always works on d2 = 32 columns:
+    // a smaller hidden2 is zero-padded at this boundary.  Zero columns of W2 and zero rows / columns of the decoder
+    // variables give zero embedding columns, zero gradients for the padding and (m = v = 0) no Adam movement, so
+    // the padded model IS the hidden2-wide model, term by term.
+    int d2u = 0;
     std::vector<NodeType> types;
     std::vector<Group> groups;
     std::vector<std::pair<int, int>> flat;  // r -> (group, k)
@@ -1237,9 +1242,10 @@ long long param_floats_per_relation(dgn_graph *g, int kind, int group) {
     Group &G = g->groups[group];
     switch (kind) {
         case DGN_PARAM_W1: return (long long)G.F_j * g->d1;
-        case DGN_PARAM_W2: return (long long)g->d1 * g->d2;
-        case DGN_PARAM_DEC_GLOBAL: return (long long)g->d2 * g->d2;
-        case DGN_PARAM_DEC_LOCAL: return (long long)G.loc_per_rel;
+        case DGN_PARAM_W2: return (long long)g->d1 * g->d2u;
+        case DGN_PARAM_DEC_GLOBAL: return (long long)g->d2u * g->d2u;
+        case DGN_PARAM_DEC_LOCAL:
+            return G.decoder == DGN_DEC_BILINEAR ? (long long)g->d2u * g->d2u : G.loc_per_rel ? (long long)g->d2u : 0;
         default: DGN_FAIL(DGN_ERR_INVALID, "unknown parameter kind %d", kind);
     }
     return 0;
@@ -1456,7 +1462,7 @@ extern "C" int dgn_graph_create(dgn_graph **out, int device, int n_types, const 
     DGN_API_BEGIN
     DGN_REQUIRE(out && n_nodes && feat_dim && group_ij && group_K && group_decoder, "null argument");
     DGN_REQUIRE(n_types > 0 && n_groups > 0, "need at least one node type and one group");
-    if (hidden2 != 32) DGN_FAIL(DGN_ERR_UNSUPPORTED, "hidden2 = %d is not supported (must be 32)", hidden2);
+    if (hidden2 < 1 || hidden2 > 32) DGN_FAIL(DGN_ERR_UNSUPPORTED, "hidden2 = %d is not supported (1 .. 32)", hidden2);
     if (hidden1 != 32 && hidden1 != 64 && hidden1 != 128)
         DGN_FAIL(DGN_ERR_UNSUPPORTED, "hidden1 = %d is not supported (32, 64 or 128)", hidden1);
     int n_dev = 0;
@@ -1471,7 +1477,7 @@ extern "C" int dgn_graph_create(dgn_graph **out, int device, int n_types, const 
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
     g->n_sm = prop.multiProcessorCount;
-    g->n_types = n_types, g->n_groups = n_groups, g->d1 = hidden1, g->d2 = hidden2, g->P1 = hidden1 / 32;
+    g->n_types = n_types, g->n_groups = n_groups, g->d1 = hidden1, g->d2 = 32, g->d2u = hidden2, g->P1 = hidden1 / 32;
     g->types.resize(n_types);
     for (int t = 0; t < n_types; ++t) {
         DGN_REQUIRE(n_nodes[t] > 0 && feat_dim[t] > 0, "node type %d: empty", t);
@@ -1800,23 +1806,43 @@ void param_io(dgn_graph *g, float *arena, int kind, int group, int k, float *val
     const long long nk = kind == DGN_PARAM_DEC_GLOBAL ? 1 : (k < 0 ? G.K : 1);
     DGN_REQUIRE(n == nk * per, "parameter kind %d group %d k %d: got %lld floats, expected %lld", kind, group, k, (long long)n, nk * per);
     CUDA_CHECK(cudaStreamSynchronize(g->stream));
-    if (!encoder || !G.partitioned) {
+    const bool padded = kind != DGN_PARAM_W1 && g->d2u != g->d2;  // hidden2 < 32: zero-padded on the device
+    if (!padded && (!encoder || !G.partitioned)) {
         ParamSpan s = locate_param(g, kind, group, k);
         if (write) arena_write(g, arena, s, values);
         else arena_read(g, arena, s, values);
         return;
     }
+    // logical [rows_u, d2u] <-> device [rows_p, 32] of ONE relation's variable
+    long long rows_u = 1, rows_p = 1;
+    if (kind == DGN_PARAM_W2) rows_u = rows_p = g->d1;
+    else if (kind == DGN_PARAM_DEC_GLOBAL || G.decoder == DGN_DEC_BILINEAR) rows_u = g->d2u, rows_p = g->d2;
+    std::vector<float> wide(padded ? (size_t)rows_p * g->d2 : 0);
     const int k0 = k < 0 ? 0 : k;
     for (int kk = k0; kk < k0 + nk; ++kk) {
         float *v = values + (size_t)(kk - k0) * per;
-        const int l = G.loc_index[kk];
+        const int l = encoder && G.partitioned ? G.loc_index[kk] : kk;
         if (l < 0) {
             if (!write) memset(v, 0, (size_t)per * sizeof(float));
             continue;
         }
         ParamSpan s = locate_param(g, kind, group, l);
-        if (write) arena_write(g, arena, s, v);
-        else arena_read(g, arena, s, v);
+        if (!padded) {
+            if (write) arena_write(g, arena, s, v);
+            else arena_read(g, arena, s, v);
+            continue;
+        }
+        DGN_REQUIRE(s.count == rows_p * g->d2 && per == rows_u * g->d2u, "internal: padded span of kind %d", kind);
+        if (write) {
+            std::fill(wide.begin(), wide.end(), 0.f);
+            for (long long r = 0; r < rows_u; ++r)
+                std::copy(v + r * g->d2u, v + (r + 1) * g->d2u, wide.begin() + r * g->d2);
+            arena_write(g, arena, s, wide.data());
+        } else {
+            arena_read(g, arena, s, wide.data());
+            for (long long r = 0; r < rows_u; ++r)
+                std::copy(wide.begin() + r * g->d2, wide.begin() + r * g->d2 + g->d2u, v + r * g->d2u);
+        }
     }
 }
 }  // namespace
@@ -1915,7 +1941,14 @@ extern "C" int dgn_comm_init(dgn_graph *g, int rank, int world) {
 extern "C" int dgn_params_count(dgn_graph *g, int64_t *n_out) {
     DGN_API_BEGIN
     DGN_REQUIRE(g && n_out, "null argument");
-    *n_out = (int64_t)g->n_params;
+    int64_t n = 0;  // floats as the caller counts them (hidden2 columns, not the padded 32)
+    for (int gi = 0; gi < g->n_groups; ++gi) {
+        Group &G = g->groups[gi];
+        n += (int64_t)G.Kl * (param_floats_per_relation(g, DGN_PARAM_W1, gi) + param_floats_per_relation(g, DGN_PARAM_W2, gi));
+        n += (int64_t)G.K * param_floats_per_relation(g, DGN_PARAM_DEC_LOCAL, gi);
+        if (G.decoder == DGN_DEC_DEDICOM) n += param_floats_per_relation(g, DGN_PARAM_DEC_GLOBAL, gi);
+    }
+    *n_out = n;
     DGN_API_END
 }
 
@@ -2353,11 +2386,15 @@ extern "C" int dgn_tensor_get(dgn_graph *g, int which, int index, float *out, in
         } break;
         default: DGN_FAIL(DGN_ERR_INVALID, "unknown tensor id %d", which);
     }
-    DGN_REQUIRE(n == rows * 32 * P, "tensor %d[%d]: got room for %lld floats, need %lld", which, index, (long long)n, rows * 32 * P);
+    const bool layer1 = which == DGN_TENSOR_HIDDEN1 || which == DGN_TENSOR_LAYER1_GROUP;
+    const long long cols = layer1 ? g->d1 : g->d2u;  // what the caller sees; the device holds 32 * P columns
+    DGN_REQUIRE(n == rows * cols, "tensor %d[%d]: got room for %lld floats, need %lld", which, index, (long long)n, rows * cols);
     CUDA_CHECK(cudaStreamSynchronize(g->stream));
-    std::vector<float> tmp((size_t)n);
-    CUDA_CHECK(cudaMemcpy(tmp.data(), src, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
-    unpack_panels(tmp.data(), out, rows, P);
+    std::vector<float> tmp((size_t)rows * 32 * P);
+    CUDA_CHECK(cudaMemcpy(tmp.data(), src, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    if (cols == 32 * P) unpack_panels(tmp.data(), out, rows, P);
+    else  // hidden2 < 32: one panel, the padding columns (zeros) stay behind
+        for (long long r = 0; r < rows; ++r) std::copy(tmp.begin() + r * 32, tmp.begin() + r * 32 + cols, out + r * cols);
     DGN_API_END
 }
 
@@ -2367,10 +2404,16 @@ extern "C" int dgn_tensor_set(dgn_graph *g, int which, int index, const float *v
     DGN_REQUIRE(which == DGN_TENSOR_EMBEDDINGS, "only the embeddings can be set (tensor id %d)", which);
     DGN_REQUIRE(index >= 0 && index < g->n_types, "node type %d out of range", index);
     NodeType &T = g->types[index];
-    DGN_REQUIRE(n == (int64_t)T.n * g->d2, "embeddings[%d]: got %lld floats, need %lld", index, (long long)n, (long long)T.n * g->d2);
+    DGN_REQUIRE(n == (int64_t)T.n * g->d2u, "embeddings[%d]: got %lld floats, need %lld", index, (long long)n, (long long)T.n * g->d2u);
     CUDA_CHECK(cudaSetDevice(g->device));
     CUDA_CHECK(cudaStreamSynchronize(g->stream));
-    CUDA_CHECK(cudaMemcpy(T.Z, values, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));  // hidden2 == 32: one panel
+    if (g->d2u == g->d2) {  // one panel = row-major
+        CUDA_CHECK(cudaMemcpy(T.Z, values, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+    } else {
+        std::vector<float> wide((size_t)T.n * g->d2, 0.f);
+        for (long long r = 0; r < T.n; ++r) std::copy(values + r * g->d2u, values + (r + 1) * g->d2u, wide.begin() + r * g->d2);
+        CUDA_CHECK(cudaMemcpy(T.Z, wide.data(), wide.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     DGN_API_END
 }
 
@@ -2388,8 +2431,12 @@ extern "C" int dgn_relation_matrices(dgn_graph *g, int r, float *glb_out, float 
                                  G.loc_per_rel ? g->params + G.loc_off + (size_t)k * G.loc_per_rel : nullptr, tmp, tmp + n, g->stream);
         g->launches++;
         CUDA_CHECK(cudaStreamSynchronize(g->stream));
-        CUDA_CHECK(cudaMemcpy(glb_out, tmp, n * sizeof(float), cudaMemcpyDeviceToHost));
-        CUDA_CHECK(cudaMemcpy(loc_out, tmp + n, n * sizeof(float), cudaMemcpyDeviceToHost));
+        std::vector<float> both(2 * n);
+        CUDA_CHECK(cudaMemcpy(both.data(), tmp, 2 * n * sizeof(float), cudaMemcpyDeviceToHost));
+        for (int m = 0; m < 2; ++m)  // the leading [hidden2, hidden2] block of the device's [32, 32]
+            for (int r = 0; r < g->d2u; ++r)
+                std::copy(both.begin() + m * n + (size_t)r * g->d2, both.begin() + m * n + (size_t)r * g->d2 + g->d2u,
+                          (m ? loc_out : glb_out) + (size_t)r * g->d2u);
     } catch (...) {
         cudaFree(tmp);
         throw;

@@ -41,8 +41,12 @@ __device__ __forceinline__ float relation_entry(int decoder, const float *glb, c
 }
 
 constexpr float kFixedScale = 1099511627776.f;  // 2^40
-__device__ __forceinline__ void fixed_add(long long *dst, float x) {
+constexpr float kFixedLimit = 4194304.f;        // 2^22: |x| below it keeps 2^40 x (and sums of 2 * B of them) inside int64
+// Returns false when x cannot be represented (too large, inf or NaN): the caller turns the step's loss into NaN,
+// which is what the reference's float arithmetic would show for a diverged model, instead of a finite, wrong dZ.
+__device__ __forceinline__ bool fixed_add(long long *dst, float x) {
     atomicAdd(reinterpret_cast<unsigned long long *>(dst), (unsigned long long)__float2ll_rn(x * kFixedScale));
+    return fabsf(x) < kFixedLimit;
 }
 __global__ void fixed_to_float_kernel(const long long *__restrict__ q, float *__restrict__ out, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -90,6 +94,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 1) decode_kernel(const StepDyn
 #pragma unroll
     for (int p = 0; p < D; ++p) dMcol[p] = 0.f;
     float loss = 0.f;
+    bool ok = true;  // every dZ contribution fits the fixed-point range
 
     for (int b = b0 + warp; b < b1; b += n_warps) {
         const int u = a.batch[2 * b], v = a.batch[2 * b + 1];
@@ -126,10 +131,11 @@ __global__ void __launch_bounds__(kDecodeThreads, 1) decode_kernel(const StepDyn
         }
         // nodes repeat inside a batch: the scatter-add runs on 2^-40 fixed-point integers, whose sums do not
         // depend on the order of the atomics (float atomics would make the replicas of a multi-GPU run drift)
-        if (dpos != 0.f) fixed_add(a.dZi + (size_t)u * D + lane, dpos * av);
-        if (dneg != 0.f) fixed_add(a.dZi + (size_t)ng * D + lane, dneg * av);
-        if (dpos != 0.f || dneg != 0.f) fixed_add(a.dZj + (size_t)v * D + lane, cv);
+        if (dpos != 0.f) ok &= fixed_add(a.dZi + (size_t)u * D + lane, dpos * av);
+        if (dneg != 0.f) ok &= fixed_add(a.dZi + (size_t)ng * D + lane, dneg * av);
+        if (dpos != 0.f || dneg != 0.f) ok &= fixed_add(a.dZj + (size_t)v * D + lane, cv);
     }
+    const int overflow = __syncthreads_or(!ok);  // every thread of the CTA gets here (no early exit above)
 
     if (lane == 0) loss_w[warp] = loss;
     for (int w = 0; w < n_warps; ++w) {  // ordered reduction over warps
@@ -145,7 +151,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 1) decode_kernel(const StepDyn
     if (threadIdx.x == 0) {
         float s = 0.f;
         for (int w = 0; w < n_warps; ++w) s += loss_w[w];
-        part[D * D] = s;
+        part[D * D] = overflow ? __int_as_float(0x7fc00000) : s;  // NaN poisons the sum over CTAs
     }
     __threadfence();
     __syncthreads();

@@ -38,22 +38,22 @@ def assert_close(a, b, tol, what=None):
 
 
 class Case(object):
-    def __init__(self, inputs, iterator_seed=0, param_seed=1, batch_size=512, val_test_size=0.05, hidden1=64):
+    def __init__(self, inputs, iterator_seed=0, param_seed=1, batch_size=512, val_test_size=0.05, hidden1=64, hidden2=32):
         self.inputs = inputs
         np.random.seed(iterator_seed)
         self.it = EdgeMinibatchIterator(inputs.adj_mats, inputs.feat, inputs.edge_types, {}, batch_size=batch_size,
                                         val_test_size=val_test_size)
-        self.graph = O.Graph.from_iterator(self.it, inputs.edge_type2decoder, hidden1=hidden1)
+        self.graph = O.Graph.from_iterator(self.it, inputs.edge_type2decoder, hidden1=hidden1, hidden2=hidden2)
         self.p32 = O.init_params(self.graph, np.random.RandomState(param_seed))
         self.p64 = O.cast_params(self.p32, np.float64)
         self.batch_size = batch_size
         self.placeholders = {k: k for k in PLACEHOLDER_KEYS}
-        self.hidden1 = hidden1
+        self.hidden1, self.hidden2 = hidden1, hidden2
 
     def engine(self):
         from decagon_b200.engine import Engine
         eng = Engine(self.inputs.n_nodes, self.inputs.num_feat, self.inputs.edge_types, self.inputs.edge_type2decoder,
-                     hidden1=self.hidden1)
+                     hidden1=self.hidden1, hidden2=self.hidden2)
         eng.load_iterator(self.it, self.inputs.degrees)
         eng.set_params(self.p32)
         return eng

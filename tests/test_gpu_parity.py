@@ -279,6 +279,73 @@ def test_hidden_sizes():
         eng.close()
 
 
+def test_diverged_decoder_reports_nan_loss():
+    """dZ is scattered on 2^-40 fixed-point integers (sums independent of the order of the atomics, DESIGN.md
+    section 4); a contribution of 2^22 or more does not fit.  The step then reports a NaN loss -- what the
+    reference's float arithmetic shows for a diverged model -- instead of a finite loss over wrong gradients."""
+    c = Case(datasets.toy_graph())
+    eng = c.engine()
+    r, batch = c.batches(1)[0]
+    g, k = c.graph.flat[r]
+    assert np.isfinite(float(eng.train_step(r, batch, negatives=None, seed=SEED, step=0, apply_update=False)))
+    eng.set_param(_lib.PARAM_DEC_LOCAL, g, None, c.p32['D'][g] * np.float32(1e8))
+    assert np.isnan(float(eng.train_step(r, batch, negatives=None, seed=SEED, step=0, apply_update=False)))
+    eng.set_param(_lib.PARAM_DEC_LOCAL, g, None, c.p32['D'][g])
+    assert np.isfinite(float(eng.train_step(r, batch, negatives=None, seed=SEED, step=1, apply_update=False)))
+    eng.close()
+
+
+@pytest.mark.parametrize('h2', [16, 5])
+def test_hidden2_below_32(h2):
+    """``model.py:80`` takes any ``FLAGS.hidden2``.  The device works on 32 embedding columns; a smaller hidden2 is
+    zero-padded at the C ABI (W2 columns, decoder rows / columns), which is the hidden2-wide model term by term:
+    every tensor crosses the boundary in its hidden2-wide shape and matches the hidden2-wide oracle -- all four
+    decoder kinds, both losses, all-pairs scores, and a multi-step Adam run (padding that leaked into the
+    parameters would show up in the later losses)."""
+    c = Case(datasets.toy_graph(common.MIXED_DECODERS), hidden2=h2)
+    eng = c.engine()
+    assert eng.n_params() == sum(v.size for name in c.p32 for v in c.p32[name].values())
+    back = eng.get_params()
+    for name in c.p32:
+        for g in c.p32[name]:
+            assert back[name][g].shape == c.p32[name][g].shape and np.array_equal(back[name][g], c.p32[name][g])
+    Z = check_forward(c, eng, 0.1, 0)
+    assert all(eng.embeddings(t).shape == (c.graph.n_nodes[t], h2) for t in Z)
+    for step, g in enumerate(c.graph.groups):
+        batch = np.asarray(c.it.train_edges[g][0][:256], dtype=np.int32)
+        check_grads(c, eng, eng.flat_index[(g, 0)], batch, 0.1, step, 'hinge' if step % 2 == 0 else 'xent')
+    Z = check_forward(c, eng, 0.0, 0)
+    for g in c.graph.groups:
+        r = eng.flat_index[(g, 0)]
+        assert rel_err(eng.predict(r), O.predict_all_pairs(c.graph, c.p64, Z, g, 0)) <= TOL, g
+        glb, loc = O.relation_matrices(c.graph, c.p64, g, 0)
+        eglb, eloc = eng.relation_matrices(r)
+        assert eglb.shape == (h2, h2) and rel_err(eglb, glb) <= 1e-7 and rel_err(eloc, loc) <= 1e-7
+    # saved embeddings loaded back (NpPredictor's use case) are hidden2-wide too
+    rng = np.random.RandomState(h2)
+    Zs = {t: rng.randn(c.graph.n_nodes[t], h2).astype(np.float32) for t in Z}
+    for t in Zs:
+        eng.set_embeddings(t, Zs[t])
+        assert np.array_equal(eng.embeddings(t), Zs[t])
+    g = c.graph.groups[-1]
+    want = O.predict_all_pairs(c.graph, c.p64, {t: Zs[t].astype(np.float64) for t in Zs}, g, 0)
+    assert rel_err(eng.predict(eng.flat_index[(g, 0)]), want) <= TOL
+    eng.reset_optimizer()
+    p = O.cast_params(c.p32, np.float64)
+    adam = O.AdamTF1(p, lr=1e-3)
+    losses_dev, losses_ref = [], []
+    for step, (r, batch) in enumerate(c.batches(8)):
+        g, k = c.graph.flat[r]
+        negs = O.sample_negatives(c.thresholds(r), len(batch), r, step, SEED)
+        masks = O.masks_for(c.graph, 0.1, step, SEED)
+        loss, _, _, grads, _ = O.train_step_grads(c.graph, p, g, k, batch, negs, 0.1, masks, 'hinge')
+        adam.apply(p, grads)
+        losses_ref.append(loss)
+        losses_dev.append(float(eng.train_step(r, batch, negatives=None, seed=SEED, step=step, dropout=0.1)))
+    assert rel_err(losses_dev, losses_ref) <= 1e-4, (losses_dev, losses_ref)
+    eng.close()
+
+
 @pytest.mark.parametrize('h1', [32, 64])
 def test_dense_layer2_tensor_cores_match_cuda_cores(h1):
     """project / dw2 / dh on tcgen05 (TF32 split, dense_tc.cu; the default) and on the CUDA cores
