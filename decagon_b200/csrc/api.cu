@@ -378,11 +378,12 @@ struct Phase {
 struct dgn_graph {
     int device = 0, n_sm = 148;
     int n_types = 0, n_groups = 0, R = 0, d1 = 0, d2 = 0, P1 = 0;
-    // hidden2 as the caller passed it (model.py:80 takes any FLAGS.hidden2); the device always works on d2 = 32 columns:
-    // a smaller hidden2 is zero-padded at this boundary.  Zero columns of W2 and zero rows / columns of the decoder
-    // variables give zero embedding columns, zero gradients for the padding and (m = v = 0) no Adam movement, so
-    // the padded model IS the hidden2-wide model, term by term.
-    int d2u = 0;
+    // hidden1 / hidden2 as the caller passed them (model.py:68,80 take any FLAGS value); the device works on
+    // d1 in {32, 64, 128} and d2 = 32 columns: smaller sizes are zero-padded at this boundary.  Zero columns of
+    // W1 / W2, zero rows of W2 and zero rows / columns of the decoder variables give zero hidden / embedding columns
+    // (relu(0) = 0, zeros add nothing to a norm), zero gradients for the padding and (m = v = 0) no Adam movement, so
+    // the padded model IS the caller's model, term by term.
+    int d1u = 0, d2u = 0;
     std::vector<NodeType> types;
     std::vector<Group> groups;
     std::vector<std::pair<int, int>> flat;  // r -> (group, k)
@@ -1186,13 +1187,13 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam, b
 }
 
 // logical [K][rows][32 P] row-major <-> device [P][K * rows][32]
-void pack_panels(const float *src, float *dst, long long stacked_rows, int P) {
-    const int d = 32 * P;
+// row-major [rows, d] (d <= 32 * P columns; the panels' remaining columns are padding) <-> panel layout [P][rows][32]
+void pack_panels(const float *src, float *dst, long long stacked_rows, int P, int d) {
+    if (d < 32 * P) std::fill(dst, dst + (size_t)P * stacked_rows * 32, 0.f);
     for (long long r = 0; r < stacked_rows; ++r)
         for (int c = 0; c < d; ++c) dst[((size_t)(c >> 5) * stacked_rows + r) * 32 + (c & 31)] = src[(size_t)r * d + c];
 }
-void unpack_panels(const float *src, float *dst, long long stacked_rows, int P) {
-    const int d = 32 * P;
+void unpack_panels(const float *src, float *dst, long long stacked_rows, int P, int d) {
     for (long long r = 0; r < stacked_rows; ++r)
         for (int c = 0; c < d; ++c) dst[(size_t)r * d + c] = src[((size_t)(c >> 5) * stacked_rows + r) * 32 + (c & 31)];
 }
@@ -1241,8 +1242,8 @@ ParamSpan locate_param(dgn_graph *g, int kind, int group, int k) {
 long long param_floats_per_relation(dgn_graph *g, int kind, int group) {
     Group &G = g->groups[group];
     switch (kind) {
-        case DGN_PARAM_W1: return (long long)G.F_j * g->d1;
-        case DGN_PARAM_W2: return (long long)g->d1 * g->d2u;
+        case DGN_PARAM_W1: return (long long)G.F_j * g->d1u;
+        case DGN_PARAM_W2: return (long long)g->d1u * g->d2u;
         case DGN_PARAM_DEC_GLOBAL: return (long long)g->d2u * g->d2u;
         case DGN_PARAM_DEC_LOCAL:
             return G.decoder == DGN_DEC_BILINEAR ? (long long)g->d2u * g->d2u : G.loc_per_rel ? (long long)g->d2u : 0;
@@ -1258,7 +1259,7 @@ void arena_write(dgn_graph *g, float *arena, const ParamSpan &s, const float *va
     }
     // panel p of rows [row0, row0 + rows) is contiguous on the device
     std::vector<float> tmp((size_t)s.count);
-    pack_panels(values, tmp.data(), s.rows, g->P1);
+    pack_panels(values, tmp.data(), s.rows, g->P1, g->d1u);
     for (int p = 0; p < g->P1; ++p)
         CUDA_CHECK(cudaMemcpy(arena + s.off + ((size_t)p * s.stacked_rows + s.row0) * 32, tmp.data() + (size_t)p * s.rows * 32,
                               (size_t)s.rows * 32 * sizeof(float), cudaMemcpyHostToDevice));
@@ -1274,7 +1275,7 @@ void arena_read(dgn_graph *g, const float *arena, const ParamSpan &s, float *val
     for (int p = 0; p < g->P1; ++p)
         CUDA_CHECK(cudaMemcpy(tmp.data() + (size_t)p * s.rows * 32, arena + s.off + ((size_t)p * s.stacked_rows + s.row0) * 32,
                               (size_t)s.rows * 32 * sizeof(float), cudaMemcpyDeviceToHost));
-    unpack_panels(tmp.data(), values, s.rows, g->P1);
+    unpack_panels(tmp.data(), values, s.rows, g->P1, g->d1u);
 }
 
 void drop_step_graphs(dgn_graph *g) {
@@ -1463,8 +1464,7 @@ extern "C" int dgn_graph_create(dgn_graph **out, int device, int n_types, const 
     DGN_REQUIRE(out && n_nodes && feat_dim && group_ij && group_K && group_decoder, "null argument");
     DGN_REQUIRE(n_types > 0 && n_groups > 0, "need at least one node type and one group");
     if (hidden2 < 1 || hidden2 > 32) DGN_FAIL(DGN_ERR_UNSUPPORTED, "hidden2 = %d is not supported (1 .. 32)", hidden2);
-    if (hidden1 != 32 && hidden1 != 64 && hidden1 != 128)
-        DGN_FAIL(DGN_ERR_UNSUPPORTED, "hidden1 = %d is not supported (32, 64 or 128)", hidden1);
+    if (hidden1 < 1 || hidden1 > 128) DGN_FAIL(DGN_ERR_UNSUPPORTED, "hidden1 = %d is not supported (1 .. 128)", hidden1);
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
         cudaGetLastError();
@@ -1477,7 +1477,8 @@ extern "C" int dgn_graph_create(dgn_graph **out, int device, int n_types, const 
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
     g->n_sm = prop.multiProcessorCount;
-    g->n_types = n_types, g->n_groups = n_groups, g->d1 = hidden1, g->d2 = 32, g->d2u = hidden2, g->P1 = hidden1 / 32;
+    g->n_types = n_types, g->n_groups = n_groups, g->d1u = hidden1, g->d2u = hidden2;
+    g->d1 = hidden1 <= 32 ? 32 : hidden1 <= 64 ? 64 : 128, g->d2 = 32, g->P1 = g->d1 / 32;  // the kernels' panel counts: 1, 2, 4
     g->types.resize(n_types);
     for (int t = 0; t < n_types; ++t) {
         DGN_REQUIRE(n_nodes[t] > 0 && feat_dim[t] > 0, "node type %d: empty", t);
@@ -1806,7 +1807,8 @@ void param_io(dgn_graph *g, float *arena, int kind, int group, int k, float *val
     const long long nk = kind == DGN_PARAM_DEC_GLOBAL ? 1 : (k < 0 ? G.K : 1);
     DGN_REQUIRE(n == nk * per, "parameter kind %d group %d k %d: got %lld floats, expected %lld", kind, group, k, (long long)n, nk * per);
     CUDA_CHECK(cudaStreamSynchronize(g->stream));
-    const bool padded = kind != DGN_PARAM_W1 && g->d2u != g->d2;  // hidden2 < 32: zero-padded on the device
+    // zero-padded on the device (W1 pads inside arena_write / arena_read: its panels are packed there anyway)
+    const bool padded = kind != DGN_PARAM_W1 && (g->d2u != g->d2 || (kind == DGN_PARAM_W2 && g->d1u != g->d1));
     if (!padded && (!encoder || !G.partitioned)) {
         ParamSpan s = locate_param(g, kind, group, k);
         if (write) arena_write(g, arena, s, values);
@@ -1815,7 +1817,7 @@ void param_io(dgn_graph *g, float *arena, int kind, int group, int k, float *val
     }
     // logical [rows_u, d2u] <-> device [rows_p, 32] of ONE relation's variable
     long long rows_u = 1, rows_p = 1;
-    if (kind == DGN_PARAM_W2) rows_u = rows_p = g->d1;
+    if (kind == DGN_PARAM_W2) rows_u = g->d1u, rows_p = g->d1;
     else if (kind == DGN_PARAM_DEC_GLOBAL || G.decoder == DGN_DEC_BILINEAR) rows_u = g->d2u, rows_p = g->d2;
     std::vector<float> wide(padded ? (size_t)rows_p * g->d2 : 0);
     const int k0 = k < 0 ? 0 : k;
@@ -2387,14 +2389,12 @@ extern "C" int dgn_tensor_get(dgn_graph *g, int which, int index, float *out, in
         default: DGN_FAIL(DGN_ERR_INVALID, "unknown tensor id %d", which);
     }
     const bool layer1 = which == DGN_TENSOR_HIDDEN1 || which == DGN_TENSOR_LAYER1_GROUP;
-    const long long cols = layer1 ? g->d1 : g->d2u;  // what the caller sees; the device holds 32 * P columns
+    const long long cols = layer1 ? g->d1u : g->d2u;  // what the caller sees; the device holds 32 * P columns
     DGN_REQUIRE(n == rows * cols, "tensor %d[%d]: got room for %lld floats, need %lld", which, index, (long long)n, rows * cols);
     CUDA_CHECK(cudaStreamSynchronize(g->stream));
     std::vector<float> tmp((size_t)rows * 32 * P);
     CUDA_CHECK(cudaMemcpy(tmp.data(), src, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
-    if (cols == 32 * P) unpack_panels(tmp.data(), out, rows, P);
-    else  // hidden2 < 32: one panel, the padding columns (zeros) stay behind
-        for (long long r = 0; r < rows; ++r) std::copy(tmp.begin() + r * 32, tmp.begin() + r * 32 + cols, out + r * cols);
+    unpack_panels(tmp.data(), out, rows, P, (int)cols);  // the padding columns (zeros) stay behind
     DGN_API_END
 }
 

@@ -81,10 +81,12 @@ int dgn_sampler_thresholds(const double *degrees, int32_t n, uint32_t *threshold
 
 /* DecagonModel.__init__ (model.py:48-62): edge_types -> groups / K, num_feat -> feat_dim,
  * FLAGS.hidden1 / hidden2 (model.py:68,80).
- * Supported: hidden1 in {32, 64, 128}, hidden2 in 1 .. 32 (anything else: DGN_ERR_UNSUPPORTED).  The device always works
- * on 32 embedding columns; a smaller hidden2 is zero-padded INSIDE the library (columns of W2, rows / columns of the
- * decoder variables), which is the hidden2-wide model term by term: padded columns stay exactly zero through forward,
- * backward and Adam.  Every array that crosses this boundary has the caller's hidden2-wide shape.
+ * Supported: hidden1 in 1 .. 128, hidden2 in 1 .. 32 (anything else: DGN_ERR_UNSUPPORTED).  The device works on 32, 64 or
+ * 128 hidden and 32 embedding columns; other sizes are zero-padded INSIDE the library (columns of W1 / W2, rows of W2,
+ * rows / columns of the decoder variables), which is the caller's model term by term: padded columns stay exactly zero
+ * through forward, backward and Adam.  Every array that crosses this boundary has the caller's shape.  (The keep bit of
+ * element (row, col) of the layer-2 input is bit row * stride + col of the relation's dropout stream, stride = the
+ * padded hidden1.)
  * NOT supported: a per-relation activation inside the graph-convolution layers.  GraphConvolutionSparseMulti /
  * GraphConvolutionMulti default to act = tf.nn.relu applied to every relation's product BEFORE add_n
  * (layers.py:73,91,99,115); DecagonModel always constructs them with act = lambda x: x (model.py:71,82) and applies ONE

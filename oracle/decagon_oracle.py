@@ -203,7 +203,10 @@ def masks_for(graph, rate, step, seed):
     for r, (g, k) in enumerate(graph.flat):
         j = g[1]
         m1[g, k] = dropout_keep(graph.feat[j].nnz, r, 1, step, seed, rate)
-        m2[g, k] = dropout_keep(graph.n_nodes[j] * graph.d1, r, 2, step, seed, rate).reshape(graph.n_nodes[j], graph.d1)
+        # the device keeps hidden1 in 32-column panels (1, 2 or 4 of them): element (row, col) of the layer-2
+        # input is bit row * stride + col of the relation's stream
+        stride = 32 if graph.d1 <= 32 else 64 if graph.d1 <= 64 else 128
+        m2[g, k] = dropout_keep(graph.n_nodes[j] * stride, r, 2, step, seed, rate).reshape(graph.n_nodes[j], stride)[:, :graph.d1]
     return m1, m2
 
 

@@ -295,14 +295,14 @@ def test_diverged_decoder_reports_nan_loss():
     eng.close()
 
 
-@pytest.mark.parametrize('h2', [16, 5])
-def test_hidden2_below_32(h2):
-    """``model.py:80`` takes any ``FLAGS.hidden2``.  The device works on 32 embedding columns; a smaller hidden2 is
-    zero-padded at the C ABI (W2 columns, decoder rows / columns), which is the hidden2-wide model term by term:
-    every tensor crosses the boundary in its hidden2-wide shape and matches the hidden2-wide oracle -- all four
-    decoder kinds, both losses, all-pairs scores, and a multi-step Adam run (padding that leaked into the
-    parameters would show up in the later losses)."""
-    c = Case(datasets.toy_graph(common.MIXED_DECODERS), hidden2=h2)
+@pytest.mark.parametrize('h1,h2', [(64, 16), (48, 5), (100, 20)])
+def test_any_hidden_size(h1, h2):
+    """``model.py:68,80`` take any ``FLAGS.hidden1`` / ``FLAGS.hidden2``.  The device works on 32 / 64 / 128 hidden
+    and 32 embedding columns; smaller sizes are zero-padded at the C ABI (W1 / W2 columns, W2 rows, decoder rows /
+    columns), which is the caller's model term by term: every tensor crosses the boundary in the caller's shape and
+    matches the oracle of that shape -- all four decoder kinds, both losses, all-pairs scores, and a multi-step
+    Adam run (padding that leaked into the parameters would show up in the later losses)."""
+    c = Case(datasets.toy_graph(common.MIXED_DECODERS), hidden1=h1, hidden2=h2)
     eng = c.engine()
     assert eng.n_params() == sum(v.size for name in c.p32 for v in c.p32[name].values())
     back = eng.get_params()
@@ -311,6 +311,7 @@ def test_hidden2_below_32(h2):
             assert back[name][g].shape == c.p32[name][g].shape and np.array_equal(back[name][g], c.p32[name][g])
     Z = check_forward(c, eng, 0.1, 0)
     assert all(eng.embeddings(t).shape == (c.graph.n_nodes[t], h2) for t in Z)
+    assert all(eng.hidden1_of(t).shape == (c.graph.n_nodes[t], h1) for t in Z)
     for step, g in enumerate(c.graph.groups):
         batch = np.asarray(c.it.train_edges[g][0][:256], dtype=np.int32)
         check_grads(c, eng, eng.flat_index[(g, 0)], batch, 0.1, step, 'hinge' if step % 2 == 0 else 'xent')
