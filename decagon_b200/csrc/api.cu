@@ -187,7 +187,10 @@ void free_task(TaskCsr &c) {
 // Rows are sorted by length (summed over the relations, or per relation when per_rel); consecutive
 // groups of 4 go to the n_warps warps in snake order; slot s of warp w is its s-th group.  round_rpq:
 // slots per warp rounded up to an even count (the forward kernel is compiled for 2, 4, 6, 8).
-TaskCsr plan_task_csr(const std::vector<HostCsr> &rels, int n_rows, int n_warps, bool per_rel, bool round_rpq) {
+// by_address: rows keep their address order instead (4 consecutive rows per warp and slot: contiguous 512-byte
+// pieces of the output / optimizer state per access, but the lock-step padding of unsorted rows).
+TaskCsr plan_task_csr(const std::vector<HostCsr> &rels, int n_rows, int n_warps, bool per_rel, bool round_rpq,
+                      bool by_address = false) {
     const int K = (int)rels.size();
     const int n_groups = (n_rows + 3) / 4;
     int rpq = std::max(1, (n_groups + n_warps - 1) / n_warps);
@@ -203,7 +206,7 @@ TaskCsr plan_task_csr(const std::vector<HostCsr> &rels, int n_rows, int n_warps,
     std::vector<int> order((size_t)n_rows), map((size_t)n_ws * 4);
     auto make_map = [&]() {  // map[(w * rpq + s) * 4 + quarter] = row
         std::iota(order.begin(), order.end(), 0);
-        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return weight[x] > weight[y]; });
+        if (!by_address) std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return weight[x] > weight[y]; });
         std::fill(map.begin(), map.end(), -1);
         for (int j = 0; j < n_groups; ++j) {
             const int s = j / n_warps, jj = j % n_warps;
@@ -349,6 +352,12 @@ struct Group {
     TaskCsr task_fwd, task_bwd;
     SlotTable slots_bwd;
     int *wstart1 = nullptr, *wstart2 = nullptr, *wstart_bwd = nullptr;
+    // second copy of the backward streams with the rows in ADDRESS order, used by the layer-1 backward (its output rows
+    // are the 128-byte rows of dW1 / of the optimizer state: contiguous per warp instead of scattered); unused
+    // (n_warps == 0) unless DGN_BWD_ROW_ORDER is "split" (the default)
+    TaskCsr task_bwd1;
+    SlotTable slots_bwd1;
+    int *wstart_bwd1 = nullptr;
     // parameter arena offsets (floats)
     size_t w1_off = 0, w2_off = 0, glb_off = 0, loc_off = 0, loc_per_rel = 0;
     // work buffers
@@ -556,10 +565,14 @@ void free_group_device(Group &G) {
     dev_free(G.slots_bwd.rel);
     free_task(G.task_fwd);
     free_task(G.task_bwd);
+    dev_free(G.slots_bwd1.ptr);
+    dev_free(G.slots_bwd1.rel);
+    free_task(G.task_bwd1);
+    dev_free(G.wstart_bwd1);
     dev_free(G.wstart1);
     dev_free(G.wstart2);
     dev_free(G.wstart_bwd);
-    G.slots1 = SlotTable(), G.slots2 = SlotTable(), G.slots_bwd = SlotTable();
+    G.slots1 = SlotTable(), G.slots2 = SlotTable(), G.slots_bwd = SlotTable(), G.slots_bwd1 = SlotTable();
     dev_free(G.rel_ids);
     float **bufs[] = {&G.rows1, &G.rows2, &G.part1, &G.part2, &G.Y1, &G.n1, &G.Y2, &G.n2, &G.P2, &G.dS, &G.G2, &G.bwd_partial, &G.dW2part, &G.dHpart, &G.P1buf, &G.G1buf};
     for (float **b : bufs) dev_free(*b);
@@ -659,11 +672,24 @@ void build_group(dgn_graph *g, Group &G) {
     if (G.tstaged) {
         std::vector<HostCsr> relt(K);
         for (int k = 0; k < K; ++k) csr_transpose(rel[k], relt[k]);
-        G.task_bwd = plan_task_csr(relt, n_j, kTsWarps, true, false);
+        // DGN_BWD_ROW_ORDER: "length" = rows of a relation sorted by length for both backward products (4 % lock-step
+        // padding), "address" = address order for both (24 %), default "split" = layer 2 by length (gather-bound: the
+        // padding costs 125 -> 141 us) and layer 1 by address (bound by the dW1 / optimizer-state traffic: contiguous
+        // rows bring 444 -> 406 us); measured at the polypharmacy shape, DESIGN.md section 3
+        const char *row_order = getenv("DGN_BWD_ROW_ORDER");
+        const char mode = row_order ? row_order[0] : 's';
+        G.task_bwd = plan_task_csr(relt, n_j, kTsWarps, true, false, mode == 'a');
         for (int k = 0; k < K; ++k) w_bwd[k] = G.task_bwd.rel_steps[k] + 16;
         G.slots_bwd = build_slots(w_bwd, g->n_sm);
         layout_task_csr(G.task_bwd, relt, G.slots_bwd);
         G.wstart_bwd = upload_wstart(G.task_bwd, G.slots_bwd);
+        if (mode == 's') {
+            G.task_bwd1 = plan_task_csr(relt, n_j, kTsWarps, true, false, true);
+            for (int k = 0; k < K; ++k) w_bwd[k] = G.task_bwd1.rel_steps[k] + 16;
+            G.slots_bwd1 = build_slots(w_bwd, g->n_sm);
+            layout_task_csr(G.task_bwd1, relt, G.slots_bwd1);
+            G.wstart_bwd1 = upload_wstart(G.task_bwd1, G.slots_bwd1);
+        }
     }
     if (G.staged) {
         G.part1 = dev_alloc<float>((size_t)G.slots1.n_slots * panel_floats(P1, n_i));
@@ -1027,16 +1053,19 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam, b
     const int P1 = g->P1;
     const bool drop = rate > 0.f;
     const float scale = drop ? 1.f / (1.f - rate) : 1.f;
-    auto spmm_bwd = [&](Group &G, int P, float *out, long long out_rows, const uint32_t *row_mask, bool fuse_adam) {
+    auto spmm_bwd = [&](Group &G, int P, float *out, long long out_rows, const uint32_t *row_mask, bool fuse_adam, bool layer1) {
         cudaStream_t s = lane_stream(g, G.lane);
         if (G.tstaged) {
+            const bool by_address = layer1 && G.task_bwd1.n_warps > 0;  // the address-ordered copy of the streams
+            const TaskCsr &T = by_address ? G.task_bwd1 : G.task_bwd;
+            const SlotTable &S = by_address ? G.slots_bwd1 : G.slots_bwd;
             TaskArgs a = {};
-            a.hdr = G.task_bwd.hdr, a.ent = G.task_bwd.ent, a.orow = G.task_bwd.orow, a.orow_stride = G.task_bwd.orow_stride;
-            a.wstart = G.wstart_bwd;
-            a.K = G.Kl, a.n_warps = G.task_bwd.n_warps, a.rpq = G.task_bwd.rpq;
+            a.hdr = T.hdr, a.ent = T.ent, a.orow = T.orow, a.orow_stride = T.orow_stride;
+            a.wstart = by_address ? G.wstart_bwd1 : G.wstart_bwd;
+            a.K = G.Kl, a.n_warps = T.n_warps, a.rpq = T.rpq;
             a.n_out_rows = G.n_j, a.n_op_rows = G.n_i;
             a.op = G.dS, a.P = P;
-            a.slot_ptr = G.slots_bwd.ptr, a.slot_rel = G.slots_bwd.rel, a.n_slots = G.slots_bwd.n_slots;
+            a.slot_ptr = S.ptr, a.slot_rel = S.rel, a.n_slots = S.n_slots;
             a.out = out, a.mask = row_mask, a.scale = scale;
             if (fuse_adam) {
                 const size_t off = (size_t)(out - g->grads);
@@ -1093,7 +1122,7 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam, b
         }
         {
             PhaseScope ph(g, "spmm_bwd2", gi, G.lane);
-            spmm_bwd(G, 1, G.G2, (long long)G.Kl * G.n_j, nullptr, false);
+            spmm_bwd(G, 1, G.G2, (long long)G.Kl * G.n_j, nullptr, false, false);
         }
         DenseArgs a = {};
         a.H = g->types[G.j].H, a.W2 = g->params + G.w2_off, a.G2 = G.G2;
@@ -1154,7 +1183,7 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam, b
         }
         PhaseScope ph(g, "spmm_bwd1", gi, G.lane);
         if (G.gen_feat) {  // G1_k = A_k^T dS1, then dW1_k = (X_j (.) m_k / q)^T G1_k
-            spmm_bwd(G, P1, G.G1buf, (long long)G.Kl * G.n_j, nullptr, false);
+            spmm_bwd(G, P1, G.G1buf, (long long)G.Kl * G.n_j, nullptr, false, true);
             NodeType &Tj = g->types[G.j];
             FeatArgs f = {};
             f.rowptr = Tj.Xt.rowptr, f.col = Tj.Xt.col, f.val = Tj.Xt.val, f.eid = Tj.Xt_eid;
@@ -1164,7 +1193,7 @@ void run_backward(dgn_graph *g, float rate, StepDeps &D, const AdamStep &adam, b
             g->launches++;
             continue;
         }
-        spmm_bwd(G, P1, g->grads + G.w1_off, (long long)G.Kl * G.F_j, drop ? G.mask1 : nullptr, adam_fused(g, G, adam));
+        spmm_bwd(G, P1, g->grads + G.w1_off, (long long)G.Kl * G.F_j, drop ? G.mask1 : nullptr, adam_fused(g, G, adam), true);
     }
     if (draw_ahead) {
         // next step's layer-2 keep words into the OTHER buffer, on the mask stream, from the moment lane 0 has issued

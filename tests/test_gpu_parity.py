@@ -406,7 +406,8 @@ def test_general_sparse_features(graph_kind):
 
 @pytest.mark.parametrize('env', [{'DGN_SINGLE_STREAM': '1'}, {'DGN_PROJECT_SS': '1'}, {'DGN_FUSE_ADAM': '0'},
                                  {'DGN_DISABLE_TSTAGED': '1'}, {'DGN_MASK_CTAS': '1'}, {'DGN_CUDA_GRAPH': '0'},
-                                 {'DGN_SIDE_LANES': '4'}, {'DGN_GATHER_ROWSUMS': '1'}, {'DGN_MASK_AHEAD': '1'}, {'DGN_SYNC_LOSS': '1'}])
+                                 {'DGN_SIDE_LANES': '4'}, {'DGN_GATHER_ROWSUMS': '1'}, {'DGN_MASK_AHEAD': '1'}, {'DGN_SYNC_LOSS': '1'},
+                                 {'DGN_BWD_ROW_ORDER': 'length'}, {'DGN_BWD_ROW_ORDER': 'address'}])
 def test_alternate_code_paths(env):
     """The switches that select the non-default kernels / schedules (one stream instead of the lanes + mask stream,
     the shared-memory projection instead of the tensor-memory one, unfused Adam, gather-path backward) give the
