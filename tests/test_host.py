@@ -284,6 +284,21 @@ def test_no_device_fails_loudly():
         Engine(g.n_nodes, g.num_feat, g.edge_types, g.edge_type2decoder)
 
 
+def test_hidden_sizes_accepted_at_the_boundary():
+    """``model.py:68,80`` take any FLAGS.hidden1 / hidden2; the library accepts hidden1 <= 128 and hidden2 <= 32 (padded
+    to its panel widths inside) and refuses anything larger with DGN_ERR_UNSUPPORTED -- checked before a device is
+    looked for, so the refusal is observable here too."""
+    from decagon_b200.engine import Engine
+    g = datasets.toy_graph()
+    for h1, h2 in ((129, 32), (64, 33), (0, 32), (64, 0)):
+        with pytest.raises(NotImplementedError, match='not supported'):
+            Engine(g.n_nodes, g.num_feat, g.edge_types, g.edge_type2decoder, hidden1=h1, hidden2=h2)
+    if _lib.device_count() == 0:
+        for h1, h2 in ((100, 20), (1, 1), (128, 32)):
+            with pytest.raises(_lib.DecagonB200Error, match='no CPU fallback'):  # past the size check
+                Engine(g.n_nodes, g.num_feat, g.edge_types, g.edge_type2decoder, hidden1=h1, hidden2=h2)
+
+
 def test_relation_matrix_types():
     m = RelationCsrMatrix(sp.identity(4, format='csr'))
     t = m.transpose(copy=True, setId=True)
